@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the set-operation path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU glistcompare
+
+Workload (configs[1] of BASELINE.json): ``glistcompare -u`` (rule add, cut-off 1) of two sorted
+25-mer lists of ~1e9 k-mers each, 50 % overlap, on every GPU (weak scaling: rank r owns the r-th
+key range of a world-size-times-larger pair of lists, so the shards are exactly what the key-range
+splitters of section 8(e) would hand out).  A step = one pass of the hot path over the rank's shard:
+partition kernel + tile kernel (+ the allgather of per-rank output counts when N > 1).
+
+One JSON line is printed by rank 0; see README/DESIGN.md section 6 for the fields.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "input k-mers/sec merged (glistcompare -u, rule add, 2 x 25-mer lists)"
+UNIT = "k-mers/s"
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["gt4gpu", "reference"], default="gt4gpu")
+    ap.add_argument("--n-per-list", type=float, default=1e9, help="k-mers per list per GPU")
+    ap.add_argument("--overlap", type=float, default=0.5, help="|A and B| / |A|")
+    ap.add_argument("--k", type=int, default=25)
+    ap.add_argument("--op", choices=["union", "intersect", "diff"], default="union")
+    ap.add_argument("--cutoff", type=int, default=1)
+    ap.add_argument("--count-only", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=float, default=1e8, help="k-mers per list of the CPU baseline sample")
+    ap.add_argument("--ref-sample", type=float, default=4e7, help="k-mers per list per step of --impl reference")
+    ap.add_argument("--tile", type=str, default=None, help="e.g. 256x9")
+    return ap.parse_args()
+
+
+def universe_for(n_per_list: float, overlap: float):
+    """|A| = |B| = n with |A & B| = overlap * n  ->  universe M and the (a_only, b_only) shares."""
+    n_both = overlap * n_per_list
+    m = int(round(2 * n_per_list - n_both))
+    p_only = (n_per_list - n_both) / m
+    return m, p_only, p_only
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the tile kernel from the committed ncu summary of this workload, if any."""
+    p = ROOT / "profiles" / "ncu_summary.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("setop2_tile_kernel", {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in Path(self.path).read_text().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+
+def build_sample_lists(tmpdir: Path, n_per_list: float, overlap: float, k: int, seed: int = 42):
+    """First `n_per_list` k-mers per list of the workload, generated on the host (numpy twin of the
+    device generator) and written as .list files the way glistmaker would."""
+    import numpy as np
+    from genometester4_b200 import synth
+    from genometester4_b200.api import RECORD
+    m, pa, pb = universe_for(n_per_list, overlap)
+    paths = []
+    (wa, ca), (wb, cb) = synth.pair_numpy(seed, k, m, 0, m, pa, pb)
+    for name, w, c in (("A", wa, ca), ("B", wb, cb)):
+        rec = np.empty(w.size, dtype=RECORD)
+        rec["word"], rec["count"] = w, c
+        hdr = np.zeros(1, dtype=[("code", "<u4"), ("major", "<u4"), ("minor", "<u4"), ("k", "<u4"), ("n", "<u8"),
+                                 ("total", "<u8"), ("start", "<u8"), ("wb", "<u4"), ("cb", "<u4")])
+        hdr["code"], hdr["major"], hdr["minor"], hdr["k"] = 0x47543443, 4, 2, k
+        hdr["n"], hdr["total"], hdr["start"], hdr["wb"], hdr["cb"] = w.size, int(c.astype(np.uint64).sum()), 48, 8, 4
+        p = tmpdir / f"sample_{name}.list"
+        with open(p, "wb") as f:
+            f.write(hdr.tobytes())
+            f.write(rec.tobytes())
+        paths.append(p)
+    return paths, wa.size + wb.size
+
+
+def reference_binary():
+    p = ROOT / "oracle" / "_ref" / "glistcompare"
+    if not p.exists() and Path("/root/reference/src").exists():
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref"], check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return p if p.exists() else None
+
+
+def time_reference(paths, op_flag: str, cutoff: int, count_only: bool, cwd: Path) -> float:
+    exe = reference_binary()
+    args = [str(exe), str(paths[0]), str(paths[1]), op_flag, "-c", str(cutoff), "-o", str(cwd / "ref")]
+    if count_only:
+        args.append("--count_only")
+    t0 = time.perf_counter()
+    subprocess.run(args, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.perf_counter() - t0
+
+
+def time_oracle_port(paths, op: str, cutoff: int) -> float:
+    from oracle import oracle as O
+    a, b = O.read_list(paths[0]), O.read_list(paths[1])
+    t0 = time.perf_counter()
+    O.compare2(a, b, union=op == "union", intrsec=op == "intersect", diff=op == "diff", cutoff=cutoff)
+    return time.perf_counter() - t0
+
+
+OP_FLAG = {"union": "-u", "intersect": "-i", "diff": "-d"}
+
+
+def cpu_arm(n_per_list: float, overlap: float, k: int, op: str, cutoff: int, count_only: bool, repeats: int, warmup: int):
+    """Times the reference's CPU implementation on a bounded sample.  Returns (best k-mers/s, info dict, all times)."""
+    shm = Path("/dev/shm") if Path("/dev/shm").is_dir() else None
+    with tempfile.TemporaryDirectory(dir=shm) as td:
+        td = Path(td)
+        paths, n_in = build_sample_lists(td, n_per_list, overlap, k)
+        kind = "reference" if reference_binary() is not None else "port"
+        times = []
+        for it in range(warmup + repeats):
+            t = time_reference(paths, OP_FLAG[op], cutoff, count_only, td) if kind == "reference" else time_oracle_port(paths, op, cutoff)
+            if it >= warmup:
+                times.append(t)
+        best = min(times)
+    info = {"value": n_in / best, "unit": UNIT, "kind": kind,
+            "cores": 3 if kind == "reference" else 1,
+            "sample": (f"{OP_FLAG[op]}{' --count_only' if count_only else ''} of the first {n_in} k-mers of the workload "
+                       f"({n_in // 2} per list, page-cache-hot .list files in /dev/shm, best of {len(times)}); "
+                       + ("unmodified glistcompare from oracle/_ref: 1 merge thread + 2 mmap scout threads (the reference has no multi-threaded merge)"
+                          if kind == "reference" else "oracle C port, 1 thread"))}
+    return n_in, times, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_in, times, info = cpu_arm(args.ref_sample, args.overlap, args.k, args.op, args.cutoff, args.count_only,
+                                repeats=args.steps, warmup=min(args.warmup, 1))
+    ms = 1000.0 * sum(times) / len(times)
+    value = n_in / (ms / 1000.0)
+    info["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 keys / u32 counts", "data": "synthetic",
+            "config": workload_config(args, n_in // 2, n_in // 2, sample=True),
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, na, nb, sample=False):
+    return {"workload": f"glistcompare {OP_FLAG[args.op]} (rule default, cutoff {args.cutoff}"
+                        f"{', --count_only' if args.count_only else ''}) of two sorted {args.k}-mer lists, "
+                        f"~{args.n_per_list:.0e} k-mers each per GPU, {int(args.overlap * 100)}% overlap (BASELINE.json configs[1])",
+            "k": args.k, "n_a_per_gpu": int(na), "n_b_per_gpu": int(nb), "overlap": args.overlap,
+            "sharding": "key-range, one shard per GPU, no payload exchange",
+            "l2_policy": "inputs (>= 24 GB per step) exceed the 126 MB L2; no flush needed" if not sample else "cpu sample",
+            "cpu_sample": bool(sample)}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+
+def run_gt4gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import genometester4_b200 as g
+    from genometester4_b200 import api, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; genometester4_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g.init(local)
+    if args.tile:
+        nt, vt = args.tile.split("x")
+        g.set_tile(int(nt), int(vt))
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # ---- this rank's shard of the synthetic lists, generated in HBM
+    m_local, pa, pb = universe_for(args.n_per_list, args.overlap)
+    universe = m_local * world
+    (wa, ca), (wb, cb) = synth.pair_torch(42, args.k, universe, rank * m_local, (rank + 1) * m_local, pa, pb, device="cuda")
+    na, nb = wa.numel(), wb.numel()
+    la = g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), na, args.k, keepalive=(wa, ca))
+    lb = g.WordList.from_device(wb.data_ptr(), cb.data_ptr(), nb, args.k, keepalive=(wb, cb))
+    stream_name = {"union": "union", "intersect": "intrsec", "diff": "diff1"}[args.op]
+    kw = {"union": dict(find_union=1), "intersect": dict(find_intrsec=1), "diff": dict(find_diff=1)}[args.op]
+    cap = {"union": na + nb, "intersect": min(na, nb), "diff": na}[args.op]
+    out_buffers = None
+    if not args.count_only:
+        ow = torch.empty(cap, dtype=torch.int64, device="cuda")
+        oc = torch.empty(cap, dtype=torch.int32, device="cuda")
+        out_buffers = {stream_name: (ow.data_ptr(), oc.data_ptr(), cap)}
+    torch.cuda.empty_cache()
+    gather = torch.zeros(world, 2, dtype=torch.int64, device="cuda") if world > 1 else None
+
+    def step():
+        r = g.compare_wordmaps(la, lb, cutoff=args.cutoff, countonly=int(args.count_only), out_buffers=out_buffers, **kw)[stream_name]
+        if world > 1:
+            # the path's only collective: per-rank {n_out, sum} -> global record offsets + header totals
+            mine = torch.tensor([r.n_words, r.total_count], dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(gather.view(-1), mine)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    n_out = res.n_words
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    part_ms, merge_ms, launches = [], [], 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+        p_ms, m_ms, nl = g.last_timing()
+        part_ms.append(p_ms)
+        merge_ms.append(m_ms)
+        launches += nl
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    stats = torch.tensor([ms_step, statistics.mean(merge_ms), statistics.mean(part_ms)], dtype=torch.float64, device="cuda")
+    sizes = torch.tensor([na + nb, n_out], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sizes, op=dist.ReduceOp.SUM)
+    ms_step, merge_ms_max, part_ms_max = (float(x) for x in stats.tolist())
+    total_in, total_out = (int(x) for x in sizes.tolist())
+    value = total_in / (ms_step / 1000.0)
+
+    # ---- roofline of the dominant kernel (setop2_tile_kernel), per launch on this rank
+    peak, peak_src = peaks()
+    algo_bytes = 12 * (na + nb) + (0 if args.count_only else 12 * n_out)
+    achieved = algo_bytes / (statistics.mean(merge_ms) / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "setop2_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": statistics.mean(merge_ms),
+                "partition_kernel_ms": statistics.mean(part_ms),
+                "step_frac_of_peak": (algo_bytes / (ms_step / 1000.0) / 1e9) / peak}
+
+    # ---- end to end through the C ABI with HOST buffers (packed 12-byte records, pinned), copies timed
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, g, api, torch, dist, world, rank, la, lb, wa, ca, wb, cb, na, nb, n_out, cap)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            _, _, cpu = cpu_arm(args.cpu_sample, args.overlap, args.k, args.op, args.cutoff, args.count_only, repeats=1, warmup=0)
+        except Exception as exc:  # pragma: no cover
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(exc)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64 keys / u32 counts (integer compare, add mod 2^32)", "data": "synthetic",
+                "config": workload_config(args, na, nb), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches, "clocks": clocks,
+                "output_kmers": total_out, "input_kmers": total_in, "tile": args.tile or os.environ.get("GT4GPU_TILE", "256x9")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, g, api, torch, dist, world, rank, la, lb, wa, ca, wb, cb, na, nb, n_out, cap):
+    """Same step through gt4gpu_compare2_host_aos: inputs are packed .list records in pinned host memory
+    (what an mmap of the files holds), outputs land in pinned host memory; H2D, de-interleave, merge,
+    interleave and D2H all inside the timed region.  Shrinks the sample if host memory is short."""
+    import numpy as np
+    avail = 0
+    for line in Path("/proc/meminfo").read_text().splitlines():
+        if line.startswith("MemAvailable:"):
+            avail = int(line.split()[1]) * 1024
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    need = 12 * (na + nb + cap)
+    frac = 1.0
+    budget = 0.5 * avail / max(local_world, 1)
+    if need > budget:
+        frac = budget / need
+    ea, eb = int(na * frac), int(nb * frac)
+    ecap = ea + eb if args.op == "union" else (min(ea, eb) if args.op == "intersect" else ea)
+
+    def pinned_records(words_t, counts_t, n):
+        host = torch.empty(n * 12, dtype=torch.uint8, pin_memory=True)
+        dev = torch.empty(n * 12, dtype=torch.uint8, device="cuda")
+        rc = api._lib.load().gt4gpu_interleave(words_t.data_ptr(), counts_t.data_ptr(), n, dev.data_ptr())
+        assert rc == 0
+        host.copy_(dev)
+        torch.cuda.synchronize()
+        del dev
+        return host
+
+    ha = pinned_records(wa, ca, ea)
+    hb = pinned_records(wb, cb, eb)
+    hout = None if args.count_only else torch.empty(max(ecap, 1) * 12, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.empty_cache()
+    ops = {"union": api.OP_UNION, "intersect": api.OP_INTRSEC, "diff": api.OP_DIFF}[args.op]
+    sidx = {"union": 0, "intersect": 1, "diff": 2}[args.op]
+    outs = [None] * 4
+    if hout is not None:
+        outs[sidx] = (hout.data_ptr(), ecap)
+
+    def one():
+        n_o, t_o = api.compare2_host_records((ha.data_ptr(), ea), (hb.data_ptr(), eb), args.k, ops, cutoff=args.cutoff,
+                                             countonly=int(args.count_only), out_records=outs)
+        return n_o[sidx]
+
+    one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e_out = one()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([ea + eb], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dt = float(t.item())
+    return {"value": int(tot.item()) / dt, "unit": UNIT, "h2d_bytes_per_step": 12 * (ea + eb),
+            "d2h_bytes_per_step": 0 if args.count_only else 12 * int(e_out), "ms_per_step": dt * 1000.0, "steps": args.e2e_steps,
+            "api": "gt4gpu_compare2_host_aos (packed 12-byte records in pinned host memory in and out)",
+            "sample_fraction_of_workload": frac}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gt4gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

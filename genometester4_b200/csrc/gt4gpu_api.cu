@@ -1,0 +1,995 @@
+// gt4gpu_api.cu -- the C ABI declared in include/gt4gpu.h: context, containers (the gt4gpu
+// loader that turns 12-byte AoS records into SoA arrays in HBM), the merge entry points that
+// replace compare_wordmaps / union_multi / intersect_multi / gt4_write_union, result handling
+// and the host-side key-range sharding plan.  Host language: C++ compiled by nvcc, exported as
+// extern "C".  There is no CPU implementation of the merges in here: every compute entry point
+// fails with GT4GPU_ERR_CUDA when no device is available.
+#include <cuda_runtime.h>
+
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/gt4gpu.h"
+#include "gt4gpu_internal.h"
+
+using namespace gt4gpu;
+
+static_assert (sizeof (gt4gpu_header) == 48, "GT4ListHeader is 48 bytes (src/word-list.h:61-72)");
+
+struct gt4gpu_list {
+  uint64_t *words;
+  uint32_t *counts;
+  uint64_t n_words;
+  uint64_t sum_counts;
+  uint32_t word_length;
+  int owned;
+};
+
+namespace {
+
+constexpr uint32_t LIST_CODE = (uint32_t) ('G' << 24 | 'T' << 16 | '4' << 8 | 'C');   // src/word-list.c:31
+constexpr uint64_t STAGE_RECORDS = 32ull << 20;   // records per AoS staging chunk (384 MiB)
+
+struct Context {
+  bool ready = false;
+  int device = -1;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  TileShape shape = {256, 9};
+};
+Context g_ctx;
+
+thread_local char tl_error[512] = "";
+thread_local float tl_ms_partition = 0.f, tl_ms_merge = 0.f;
+thread_local uint32_t tl_launches = 0;
+thread_local cudaEvent_t tl_ev[3] = {nullptr, nullptr, nullptr};
+
+int fail (int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start (ap, fmt);
+  vsnprintf (tl_error, sizeof (tl_error), fmt, ap);
+  va_end (ap);
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString (e_)); \
+  } while (0)
+
+int ensure_ready ()
+{
+  if (g_ctx.ready) return 0;
+  return gt4gpu_init (-1);
+}
+
+int dev_alloc (void **p, size_t bytes)
+{
+  CU (cudaMallocAsync (p, bytes ? bytes : 16, g_ctx.stream));
+  return 0;
+}
+
+void dev_free (void *p)
+{
+  if (p) cudaFreeAsync (p, g_ctx.stream);
+}
+
+// One output stream of an internal merge.
+struct MergeOut {
+  uint64_t *words = nullptr;
+  uint32_t *counts = nullptr;
+  uint64_t capacity = 0;
+  uint64_t n = 0;
+  uint64_t sum = 0;
+  bool caller = false;
+};
+
+struct DevList {
+  const uint64_t *words;
+  const uint32_t *counts;
+  uint64_t n;
+};
+
+uint64_t worst_case (const SetOpParams &p, int stream, uint64_t na, uint64_t nb)
+{
+  if (p.sem == SEM_NISECT_PARTIAL || p.sem == SEM_NISECT_FINAL) return std::min (na, nb);
+  if (p.sem != SEM_PAIR) return na + nb;
+  switch (stream) {
+  case 0: return na + nb;
+  case 1: return std::min (na, nb);
+  case 2: return na;
+  default: return nb;
+  }
+}
+
+// The engine: partition + tile kernel over two device-resident SoA lists.
+int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uint32_t stream_mask, bool countonly, MergeOut out[4])
+{
+  const uint64_t total = a.n + b.n;
+  const int n_req = __builtin_popcount (stream_mask);
+  if (n_req == 0) return fail (GT4GPU_ERR_ARG, "no output stream requested");
+  const int ns = (n_req == 1) ? 1 : 4;
+  const TileShape shape = g_ctx.shape;
+  const uint64_t tile = (uint64_t) shape.threads * shape.items;
+  const uint64_t n_tiles = (total + tile - 1) / tile;
+  cudaStream_t st = g_ctx.stream;
+
+  for (int s = 0; s < 4; s++) {
+    if (!((stream_mask >> s) & 1u)) continue;
+    out[s].n = out[s].sum = 0;
+    if (countonly) continue;
+    if (!out[s].caller) {
+      out[s].capacity = worst_case (p, s, a.n, b.n);
+      int rc = dev_alloc ((void **) &out[s].words, out[s].capacity * sizeof (uint64_t));
+      if (rc) return rc;
+      rc = dev_alloc ((void **) &out[s].counts, out[s].capacity * sizeof (uint32_t));
+      if (rc) return rc;
+    }
+  }
+  if (total == 0) return 0;
+
+  // scratch: [CallHeader | descriptors | partition]
+  const size_t hdr_bytes = (sizeof (CallHeader) + 255) & ~(size_t) 255;
+  const size_t desc_bytes = countonly ? 0 : (size_t) ns * n_tiles * sizeof (uint64_t);
+  const size_t part_bytes = (n_tiles + 1) * sizeof (uint64_t);
+  unsigned char *ws = nullptr;
+  int rc = dev_alloc ((void **) &ws, hdr_bytes + desc_bytes + part_bytes);
+  if (rc) return rc;
+  CU (cudaMemsetAsync (ws, 0, hdr_bytes + desc_bytes, st));
+
+  TileArgs args;
+  memset (&args, 0, sizeof (args));
+  args.a_words = a.words; args.a_counts = a.counts; args.na = a.n;
+  args.b_words = b.words; args.b_counts = b.counts; args.nb = b.n;
+  args.hdr = reinterpret_cast<CallHeader *> (ws);
+  args.desc = reinterpret_cast<uint64_t *> (ws + hdr_bytes);
+  uint64_t *part = reinterpret_cast<uint64_t *> (ws + hdr_bytes + desc_bytes);
+  args.part = part;
+  args.n_tiles = n_tiles;
+  args.p = p;
+  args.p.ops = stream_mask;
+  args.stream0 = __builtin_ctz (stream_mask);
+  for (int s = 0; s < 4; s++) {
+    args.out_words[s] = out[s].words;
+    args.out_counts[s] = out[s].counts;
+    args.out_capacity[s] = out[s].capacity;
+  }
+
+  for (int i = 0; i < 3; i++) if (!tl_ev[i]) CU (cudaEventCreate (&tl_ev[i]));
+  CU (cudaEventRecord (tl_ev[0], st));
+  CU (launch_partition (a.words, a.n, b.words, b.n, (uint32_t) tile, n_tiles, part, st));
+  CU (cudaEventRecord (tl_ev[1], st));
+  CU (launch_setop2 (args, shape, ns, countonly, st));
+  CU (cudaEventRecord (tl_ev[2], st));
+
+  CallHeader h;
+  CU (cudaMemcpyAsync (&h, ws, sizeof (h), cudaMemcpyDeviceToHost, st));
+  CU (cudaStreamSynchronize (st));
+  dev_free (ws);
+  float ms = 0.f;
+  CU (cudaEventElapsedTime (&ms, tl_ev[0], tl_ev[1]));
+  tl_ms_partition += ms;
+  CU (cudaEventElapsedTime (&ms, tl_ev[1], tl_ev[2]));
+  tl_ms_merge += ms;
+  tl_launches += 2;
+
+  if (h.overflow) return fail (GT4GPU_ERR_CAPACITY, "output buffer too small for the merge result");
+  for (int s = 0; s < 4; s++) {
+    if (!((stream_mask >> s) & 1u)) continue;
+    for (int k = 0; k < TOTAL_SLOTS; k++) {
+      out[s].n += h.totals[s][k][0];
+      out[s].sum += h.totals[s][k][1];
+    }
+  }
+  return 0;
+}
+
+void free_out (MergeOut &o)
+{
+  if (!o.caller) {
+    dev_free (o.words);
+    dev_free (o.counts);
+  }
+  o.words = nullptr;
+  o.counts = nullptr;
+}
+
+void reset_timing ()
+{
+  tl_ms_partition = tl_ms_merge = 0.f;
+  tl_launches = 0;
+}
+
+// Header acceptance, restated from src/word-map.c:179-215 (mode 0) and
+// src/word-list-stream.c:150-168 (mode 1).
+int parse_header (const unsigned char *file, uint64_t size, int mode, const char *path, gt4gpu_header *out)
+{
+  gt4gpu_header h;
+  memset (&h, 0, sizeof (h));
+  if (mode == 0) {
+    if (size < 12) return fail (GT4GPU_ERR_FORMAT, "%s: file too small for a list header", path);
+    memcpy (&h, file, 12);
+    if (h.code != LIST_CODE) return fail (GT4GPU_ERR_FORMAT, "%s: invalid file tag (%x, should be %x)", path, h.code, LIST_CODE);
+    if (h.version_major != GT4GPU_VERSION_MAJOR)
+      return fail (GT4GPU_ERR_FORMAT, "%s: incompatible major version %u (required %u)", path, h.version_major, GT4GPU_VERSION_MAJOR);
+    const size_t take = (h.version_minor <= 2) ? 40 : 48;
+    if (size < take) return fail (GT4GPU_ERR_FORMAT, "%s: truncated header", path);
+    memcpy (&h, file, take);
+    if (h.version_minor == 0) h.list_start = 40;
+    if (h.version_minor <= 2) { h.word_bytes = 8; h.count_bytes = 4; }
+    const uint64_t need = h.list_start + h.n_words * (uint64_t) (h.word_bytes + h.count_bytes);
+    if (size < need) return fail (GT4GPU_ERR_FORMAT, "%s: file size too small (%llu, should be at least %llu)", path,
+                                  (unsigned long long) size, (unsigned long long) need);
+    // the accessors always stride 12 bytes (src/word-map.h:89-99); make sure that stays in bounds
+    if (size < h.list_start + h.n_words * 12ull) return fail (GT4GPU_ERR_FORMAT, "%s: records exceed the file", path);
+  } else {
+    if (size < 48) return fail (GT4GPU_ERR_FORMAT, "%s: could not read list header", path);
+    memcpy (&h, file, 48);
+    if (h.code != LIST_CODE) return fail (GT4GPU_ERR_FORMAT, "%s: invalid file tag (%x, should be %x)", path, h.code, LIST_CODE);
+    if (h.version_major > GT4GPU_VERSION_MAJOR)
+      return fail (GT4GPU_ERR_FORMAT, "%s: incompatible major version %u (required %u)", path, h.version_major, GT4GPU_VERSION_MAJOR);
+    if (h.version_major == 4 && h.version_minor == 0) h.list_start = 48;
+    if (size < h.list_start + h.n_words * 12ull) return fail (GT4GPU_ERR_FORMAT, "%s: records exceed the file", path);
+  }
+  *out = h;
+  return 0;
+}
+
+struct Mapping {
+  const unsigned char *data = nullptr;
+  uint64_t size = 0;
+  ~Mapping () { if (data) munmap ((void *) data, size); }
+};
+
+int map_file (const char *path, Mapping &m)
+{
+  int fd = open (path, O_RDONLY);
+  if (fd < 0) return fail (GT4GPU_ERR_IO, "cannot open %s: %s", path, strerror (errno));
+  struct stat st;
+  if (fstat (fd, &st) < 0) { close (fd); return fail (GT4GPU_ERR_IO, "cannot stat %s", path); }
+  m.size = (uint64_t) st.st_size;
+  if (m.size == 0) { close (fd); return fail (GT4GPU_ERR_FORMAT, "%s: empty file", path); }
+  void *p = mmap (NULL, m.size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close (fd);
+  if (p == MAP_FAILED) return fail (GT4GPU_ERR_IO, "cannot mmap %s: %s", path, strerror (errno));
+  m.data = static_cast<const unsigned char *> (p);
+  madvise (p, m.size, MADV_SEQUENTIAL);
+  return 0;
+}
+
+int new_list (uint64_t n, uint32_t k, gt4gpu_list **out)
+{
+  gt4gpu_list *l = static_cast<gt4gpu_list *> (calloc (1, sizeof (gt4gpu_list)));
+  if (!l) return fail (GT4GPU_ERR_ARG, "out of host memory");
+  l->n_words = n;
+  l->word_length = k;
+  l->owned = 1;
+  int rc = dev_alloc ((void **) &l->words, n * sizeof (uint64_t));
+  if (!rc) rc = dev_alloc ((void **) &l->counts, n * sizeof (uint32_t));
+  if (rc) { dev_free (l->words); free (l); return rc; }
+  *out = l;
+  return 0;
+}
+
+// host AoS -> device SoA, chunked through a device staging buffer
+int upload_aos (const void *records, uint64_t n, uint64_t *d_words, uint32_t *d_counts)
+{
+  if (n == 0) return 0;
+  const uint64_t chunk = std::min (n, STAGE_RECORDS);
+  void *stage = nullptr;
+  int rc = dev_alloc (&stage, chunk * 12);
+  if (rc) return rc;
+  const unsigned char *src = static_cast<const unsigned char *> (records);
+  cudaError_t e = cudaSuccess;
+  for (uint64_t done = 0; done < n && e == cudaSuccess; done += chunk) {
+    const uint64_t m = std::min (chunk, n - done);
+    e = cudaMemcpyAsync (stage, src + done * 12, m * 12, cudaMemcpyHostToDevice, g_ctx.stream);
+    if (e == cudaSuccess) e = launch_deinterleave (stage, m, d_words + done, d_counts + done, g_ctx.stream);
+  }
+  dev_free (stage);
+  if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.stream);
+  if (e != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "upload: %s", cudaGetErrorString (e));
+  return 0;
+}
+
+// device SoA -> host AoS, chunked; sink (ptr, bytes, first_record) consumes each chunk when given,
+// otherwise the chunks land contiguously in `records`
+template <typename Sink>
+int download_aos (const uint64_t *d_words, const uint32_t *d_counts, uint64_t n, void *records, Sink sink, bool use_sink)
+{
+  if (n == 0) return 0;
+  const uint64_t chunk = std::min<uint64_t> (n, use_sink ? (uint64_t) (4ull << 20) : STAGE_RECORDS);
+  void *stage = nullptr;
+  int rc = dev_alloc (&stage, chunk * 12);
+  if (rc) return rc;
+  void *pinned = nullptr;
+  if (use_sink) {
+    cudaError_t e = cudaMallocHost (&pinned, chunk * 12);
+    if (e != cudaSuccess) { dev_free (stage); return fail (GT4GPU_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString (e)); }
+  }
+  for (uint64_t done = 0; done < n; done += chunk) {
+    const uint64_t m = std::min (chunk, n - done);
+    cudaError_t e = launch_interleave (d_words + done, d_counts + done, m, stage, g_ctx.stream);
+    void *dst = use_sink ? pinned : static_cast<unsigned char *> (records) + done * 12;
+    if (e == cudaSuccess) e = cudaMemcpyAsync (dst, stage, m * 12, cudaMemcpyDeviceToHost, g_ctx.stream);
+    if (e == cudaSuccess && use_sink) e = cudaStreamSynchronize (g_ctx.stream);
+    if (e != cudaSuccess) {
+      dev_free (stage);
+      if (pinned) cudaFreeHost (pinned);
+      return fail (GT4GPU_ERR_CUDA, "download: %s", cudaGetErrorString (e));
+    }
+    if (use_sink) {
+      rc = sink (pinned, m * 12, done);
+      if (rc) { dev_free (stage); cudaFreeHost (pinned); return rc; }
+    }
+  }
+  dev_free (stage);
+  cudaError_t e = cudaStreamSynchronize (g_ctx.stream);
+  if (pinned) cudaFreeHost (pinned);
+  if (e != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "download: %s", cudaGetErrorString (e));
+  return 0;
+}
+
+int write_all (int fd, const void *buf, size_t bytes, int64_t offset)
+{
+  const unsigned char *p = static_cast<const unsigned char *> (buf);
+  while (bytes) {
+    ssize_t w = (offset >= 0) ? pwrite (fd, p, bytes, offset) : write (fd, p, bytes);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      return fail (GT4GPU_ERR_IO, "write failed: %s", strerror (errno));
+    }
+    p += w;
+    bytes -= (size_t) w;
+    if (offset >= 0) offset += w;
+  }
+  return 0;
+}
+
+void fill_result (gt4gpu_result *r, const MergeOut &o, uint32_t k, bool countonly)
+{
+  r->n_words = o.n;
+  r->total_count = o.sum;
+  r->word_length = k;
+  if (countonly) {
+    r->flags |= GT4GPU_RESULT_COUNT_ONLY;
+    return;
+  }
+  r->words = o.words;
+  r->counts = o.counts;
+  r->capacity = o.capacity;
+}
+
+SetOpParams nlist_params (int sem, int rule, uint32_t cutoff, uint32_t ov)
+{
+  SetOpParams p;
+  memset (&p, 0, sizeof (p));
+  p.ops = OP_UNION;
+  p.cutoff = cutoff;
+  p.count_override = ov;
+  p.rule[0] = p.rule[1] = p.rule[2] = p.rule[3] = rule;
+  p.sem = sem;
+  return p;
+}
+
+// N-list union as a balanced tree of two-list merges (add / max / number are associative and
+// commutative, so any tree reproduces union_multi's left-to-right fold, u32 wrap-around included);
+// inner nodes keep every key, the cut-off is applied by the root only.
+struct TreeNode {
+  DevList list;
+  MergeOut owned;      // valid when is_owned: an intermediate result this node must free
+  bool is_owned;
+};
+
+int union_tree (const std::vector<DevList> &leaves, int rule, uint32_t cutoff, uint32_t ov, bool countonly, MergeOut *root)
+{
+  std::vector<TreeNode> level;
+  for (const DevList &l : leaves) level.push_back (TreeNode{l, MergeOut (), false});
+  while (level.size () < 2) level.push_back (TreeNode{DevList{nullptr, nullptr, 0}, MergeOut (), false});
+  auto release = [] (TreeNode &n) { if (n.is_owned) { free_out (n.owned); n.is_owned = false; } };
+  while (level.size () > 2) {
+    std::vector<TreeNode> next;
+    for (size_t i = 0; i + 1 < level.size (); i += 2) {
+      MergeOut out[4];
+      SetOpParams p = nlist_params (SEM_NUNION_PARTIAL, rule, cutoff, ov);
+      int rc = merge2_device (level[i].list, level[i + 1].list, p, OP_UNION, false, out);
+      release (level[i]);
+      release (level[i + 1]);
+      if (rc) {
+        free_out (out[0]);
+        for (size_t k = i + 2; k < level.size (); k++) release (level[k]);
+        for (auto &n : next) release (n);
+        return rc;
+      }
+      next.push_back (TreeNode{DevList{out[0].words, out[0].counts, out[0].n}, out[0], true});
+    }
+    if (level.size () & 1) next.push_back (level.back ());   // odd one out moves up unchanged
+    level.swap (next);
+  }
+  MergeOut out[4];
+  if (root->caller) out[0] = *root;
+  SetOpParams p = nlist_params (SEM_NUNION_FINAL, rule, cutoff, ov);
+  int rc = merge2_device (level[0].list, level[1].list, p, OP_UNION, countonly, out);
+  release (level[0]);
+  release (level[1]);
+  if (rc) { free_out (out[0]); return rc; }
+  *root = out[0];
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================================ ABI
+
+extern "C" {
+
+void gt4gpu_header_init (gt4gpu_header *hdr, uint32_t word_length)
+{
+  memset (hdr, 0, sizeof (*hdr));
+  hdr->code = LIST_CODE;
+  hdr->version_major = GT4GPU_VERSION_MAJOR;
+  hdr->version_minor = GT4GPU_VERSION_MINOR;
+  hdr->word_length = word_length;
+  hdr->list_start = sizeof (gt4gpu_header);
+  hdr->word_bytes = 8;
+  hdr->count_bytes = 4;
+}
+
+int gt4gpu_init (int device)
+{
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount (&count);
+  if (e != cudaSuccess || count == 0)
+    return fail (GT4GPU_ERR_CUDA, "no CUDA device available (%s); libgt4gpu has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString (e) : "device count is 0");
+  if (device >= 0) CU (cudaSetDevice (device));
+  CU (cudaGetDevice (&g_ctx.device));
+  if (!g_ctx.own_stream) CU (cudaStreamCreateWithFlags (&g_ctx.own_stream, cudaStreamNonBlocking));
+  if (!g_ctx.stream) g_ctx.stream = g_ctx.own_stream;
+  // keep freed blocks cached in the stream-ordered pool: per-call scratch and results then cost no driver call
+  cudaMemPool_t pool;
+  CU (cudaDeviceGetDefaultMemPool (&pool, g_ctx.device));
+  uint64_t keep = UINT64_MAX;
+  CU (cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  const char *env = getenv ("GT4GPU_TILE");   // e.g. GT4GPU_TILE=256x11
+  if (env) {
+    int nt = 0, vt = 0;
+    if (sscanf (env, "%dx%d", &nt, &vt) == 2 && tile_shape_supported (nt, vt)) g_ctx.shape = TileShape{nt, vt};
+    else return fail (GT4GPU_ERR_ARG, "GT4GPU_TILE=%s is not a supported tile shape", env);
+  }
+  g_ctx.ready = true;
+  return 0;
+}
+
+void gt4gpu_shutdown (void)
+{
+  if (!g_ctx.ready) return;
+  cudaStreamSynchronize (g_ctx.stream);
+  if (g_ctx.own_stream) cudaStreamDestroy (g_ctx.own_stream);
+  g_ctx = Context ();
+}
+
+int gt4gpu_set_stream (void *cuda_stream)
+{
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  g_ctx.stream = cuda_stream ? static_cast<cudaStream_t> (cuda_stream) : g_ctx.own_stream;
+  return 0;
+}
+
+const char *gt4gpu_last_error (void) { return tl_error; }
+
+int gt4gpu_set_tile (int threads, int items_per_thread)
+{
+  if (!tile_shape_supported (threads, items_per_thread))
+    return fail (GT4GPU_ERR_ARG, "unsupported tile shape %dx%d", threads, items_per_thread);
+  g_ctx.shape = TileShape{threads, items_per_thread};
+  return 0;
+}
+
+int gt4gpu_last_timing (float *ms_partition, float *ms_merge, uint32_t *n_launches)
+{
+  if (ms_partition) *ms_partition = tl_ms_partition;
+  if (ms_merge) *ms_merge = tl_ms_merge;
+  if (n_launches) *n_launches = tl_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------ containers
+
+int gt4gpu_list_read_header (const char *path, int stream_mode, gt4gpu_header *out)
+{
+  if (!path || !out) return fail (GT4GPU_ERR_ARG, "null argument");
+  Mapping m;
+  int rc = map_file (path, m);
+  if (rc) return rc;
+  return parse_header (m.data, m.size, stream_mode, path, out);
+}
+
+int gt4gpu_list_open_range (const char *path, int stream_mode, uint64_t first, uint64_t count, gt4gpu_list **out)
+{
+  if (!path || !out) return fail (GT4GPU_ERR_ARG, "null argument");
+  Mapping m;
+  int rc = map_file (path, m);
+  if (rc) return rc;
+  gt4gpu_header h;
+  rc = parse_header (m.data, m.size, stream_mode, path, &h);
+  if (rc) return rc;
+  if (first > h.n_words) first = h.n_words;
+  if (count > h.n_words - first) count = h.n_words - first;
+  rc = ensure_ready ();
+  if (rc) return rc;
+  gt4gpu_list *l = nullptr;
+  rc = new_list (count, h.word_length, &l);
+  if (rc) return rc;
+  l->sum_counts = h.total_count;
+  rc = upload_aos (m.data + h.list_start + first * 12, count, l->words, l->counts);
+  if (rc) { gt4gpu_list_close (l); return rc; }
+  *out = l;
+  return 0;
+}
+
+int gt4gpu_list_open (const char *path, int stream_mode, gt4gpu_list **out)
+{
+  return gt4gpu_list_open_range (path, stream_mode, 0, UINT64_MAX, out);
+}
+
+int gt4gpu_list_from_host_aos (const void *records, uint64_t n_words, uint32_t word_length, gt4gpu_list **out)
+{
+  if (!out || (n_words && !records)) return fail (GT4GPU_ERR_ARG, "null argument");
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  gt4gpu_list *l = nullptr;
+  rc = new_list (n_words, word_length, &l);
+  if (rc) return rc;
+  rc = upload_aos (records, n_words, l->words, l->counts);
+  if (rc) { gt4gpu_list_close (l); return rc; }
+  *out = l;
+  return 0;
+}
+
+int gt4gpu_list_from_host_soa (const uint64_t *words, const uint32_t *counts, uint64_t n_words, uint32_t word_length, gt4gpu_list **out)
+{
+  if (!out || (n_words && (!words || !counts))) return fail (GT4GPU_ERR_ARG, "null argument");
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  gt4gpu_list *l = nullptr;
+  rc = new_list (n_words, word_length, &l);
+  if (rc) return rc;
+  if (n_words) {
+    CU (cudaMemcpyAsync (l->words, words, n_words * sizeof (uint64_t), cudaMemcpyHostToDevice, g_ctx.stream));
+    CU (cudaMemcpyAsync (l->counts, counts, n_words * sizeof (uint32_t), cudaMemcpyHostToDevice, g_ctx.stream));
+    CU (cudaStreamSynchronize (g_ctx.stream));
+  }
+  *out = l;
+  return 0;
+}
+
+int gt4gpu_list_from_device (const uint64_t *d_words, const uint32_t *d_counts, uint64_t n_words, uint32_t word_length, gt4gpu_list **out)
+{
+  if (!out || (n_words && (!d_words || !d_counts))) return fail (GT4GPU_ERR_ARG, "null argument");
+  gt4gpu_list *l = static_cast<gt4gpu_list *> (calloc (1, sizeof (gt4gpu_list)));
+  if (!l) return fail (GT4GPU_ERR_ARG, "out of host memory");
+  l->words = const_cast<uint64_t *> (d_words);
+  l->counts = const_cast<uint32_t *> (d_counts);
+  l->n_words = n_words;
+  l->word_length = word_length;
+  l->owned = 0;
+  *out = l;
+  return 0;
+}
+
+void gt4gpu_list_close (gt4gpu_list *list)
+{
+  if (!list) return;
+  if (list->owned) {
+    dev_free (list->words);
+    dev_free (list->counts);
+  }
+  free (list);
+}
+
+uint64_t gt4gpu_list_n_words (const gt4gpu_list *l) { return l ? l->n_words : 0; }
+uint32_t gt4gpu_list_word_length (const gt4gpu_list *l) { return l ? l->word_length : 0; }
+uint64_t gt4gpu_list_sum_counts (const gt4gpu_list *l) { return l ? l->sum_counts : 0; }
+const uint64_t *gt4gpu_list_device_words (const gt4gpu_list *l) { return l ? l->words : nullptr; }
+const uint32_t *gt4gpu_list_device_counts (const gt4gpu_list *l) { return l ? l->counts : nullptr; }
+
+// ------------------------------------------------------------------ merges
+
+int gt4gpu_compare2 (const gt4gpu_list *a, const gt4gpu_list *b, uint32_t ops, int rule, uint32_t cutoff,
+                     uint32_t count_override, int subtract, int countonly, gt4gpu_result out[4])
+{
+  if (!a || !b || !out) return fail (GT4GPU_ERR_ARG, "null argument");
+  if (!ops || (ops & ~15u)) return fail (GT4GPU_ERR_ARG, "ops must be a non-empty OR of GT4GPU_OP_*");
+  if (rule < GT4GPU_RULE_DEFAULT || rule > GT4GPU_RULE_NUMBER) return fail (GT4GPU_ERR_ARG, "unknown rule %d", rule);
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  reset_timing ();
+
+  SetOpParams p;
+  memset (&p, 0, sizeof (p));
+  p.ops = ops;
+  p.cutoff = cutoff;
+  p.count_override = count_override;
+  p.subtract = subtract ? 1 : 0;
+  p.sem = SEM_PAIR;
+  for (int s = 0; s < 4; s++) p.rule[s] = resolve_rule (rule, s);
+
+  MergeOut mo[4];
+  for (int s = 0; s < 4; s++) {
+    if (!((ops >> s) & 1u) || countonly) continue;
+    if (out[s].flags & GT4GPU_RESULT_CALLER_BUFFERS) {
+      mo[s].caller = true;
+      mo[s].words = out[s].words;
+      mo[s].counts = out[s].counts;
+      mo[s].capacity = out[s].capacity;
+    }
+  }
+  const DevList da{a->words, a->counts, a->n_words}, db{b->words, b->counts, b->n_words};
+  rc = merge2_device (da, db, p, ops, countonly != 0, mo);
+  if (rc) {
+    for (int s = 0; s < 4; s++) free_out (mo[s]);
+    return rc;
+  }
+  // output header word length = first list's (src/glistcompare.c:814)
+  for (int s = 0; s < 4; s++) if ((ops >> s) & 1u) fill_result (&out[s], mo[s], a->word_length, countonly != 0);
+  return 0;
+}
+
+int gt4gpu_union_multi (const gt4gpu_list *const *lists, unsigned n_lists, uint32_t cutoff, int rule,
+                        uint32_t count_override, int countonly, gt4gpu_result *out)
+{
+  if (!lists || !out || n_lists == 0) return fail (GT4GPU_ERR_ARG, "null argument");
+  // allowed rules, src/glistcompare.c:518-523
+  if (rule == GT4GPU_RULE_DEFAULT) rule = GT4GPU_RULE_ADD;
+  else if (rule != GT4GPU_RULE_ADD && rule != GT4GPU_RULE_MAX && rule != GT4GPU_RULE_NUMBER) {
+    fprintf (stderr, "union_multi: Invalid rule %u (only ADD, MAX and NUMBER allowed)\n", rule);
+    return fail (GT4GPU_ERR_ARG, "union_multi: invalid rule %d", rule);
+  }
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  reset_timing ();
+  // only non-empty lists take part (:526-533); the header word length is the first non-empty
+  // list's, or the last list's when all are empty (:535)
+  std::vector<DevList> level;
+  uint32_t k = lists[n_lists - 1]->word_length;
+  bool have_k = false;
+  for (unsigned j = 0; j < n_lists; j++) {
+    if (!lists[j]) return fail (GT4GPU_ERR_ARG, "null list");
+    if (lists[j]->n_words) {
+      if (!have_k) { k = lists[j]->word_length; have_k = true; }
+      level.push_back (DevList{lists[j]->words, lists[j]->counts, lists[j]->n_words});
+    }
+  }
+  MergeOut root;
+  if (!countonly && (out->flags & GT4GPU_RESULT_CALLER_BUFFERS)) {
+    root.caller = true;
+    root.words = out->words;
+    root.counts = out->counts;
+    root.capacity = out->capacity;
+  }
+  rc = union_tree (level, rule, cutoff, count_override, countonly != 0, &root);
+  if (rc) return rc;
+  fill_result (out, root, k, countonly != 0);
+  return 0;
+}
+
+int gt4gpu_intersect_multi (const gt4gpu_list *const *lists, unsigned n_lists, uint32_t cutoff, int rule,
+                            uint32_t count_override, int countonly, gt4gpu_result *out)
+{
+  if (!lists || !out || n_lists == 0) return fail (GT4GPU_ERR_ARG, "null argument");
+  // allowed rules, src/glistcompare.c:622-627
+  if (rule == GT4GPU_RULE_DEFAULT) rule = GT4GPU_RULE_MIN;
+  else if (rule != GT4GPU_RULE_ADD && rule != GT4GPU_RULE_MIN && rule != GT4GPU_RULE_MAX && rule != GT4GPU_RULE_NUMBER) {
+    fprintf (stderr, "intersect_multi: Invalid rule %u (only ADD, MIN, MAX and NUMBER allowed)\n", rule);
+    return fail (GT4GPU_ERR_ARG, "intersect_multi: invalid rule %d", rule);
+  }
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  reset_timing ();
+  for (unsigned j = 0; j < n_lists; j++) if (!lists[j]) return fail (GT4GPU_ERR_ARG, "null list");
+  const uint32_t k = lists[0]->word_length;   // :639
+  bool any_empty = false;
+  for (unsigned j = 0; j < n_lists; j++) any_empty |= lists[j]->n_words == 0;
+
+  MergeOut cur;       // running fold; starts as list 0 itself
+  const bool caller = !countonly && (out->flags & GT4GPU_RESULT_CALLER_BUFFERS);
+  if (any_empty) {
+    // any empty list ends the reference loop before the first comparison (:631-636)
+    MergeOut empty;
+    if (caller) { empty.caller = true; empty.words = out->words; empty.counts = out->counts; empty.capacity = out->capacity; }
+    fill_result (out, empty, k, countonly != 0);
+    return 0;
+  }
+  if (n_lists == 1) {
+    // one list: every word is "in all lists" and the fold of a single count is that count
+    // (number: the override); expressed as a final union node against an empty list
+    const int r1 = (rule == GT4GPU_RULE_NUMBER) ? GT4GPU_RULE_NUMBER : GT4GPU_RULE_ADD;
+    MergeOut mo[4];
+    if (caller) { mo[0].caller = true; mo[0].words = out->words; mo[0].counts = out->counts; mo[0].capacity = out->capacity; }
+    SetOpParams p = nlist_params (SEM_NUNION_FINAL, r1, cutoff, count_override);
+    rc = merge2_device (DevList{lists[0]->words, lists[0]->counts, lists[0]->n_words}, DevList{nullptr, nullptr, 0}, p, OP_UNION, countonly != 0, mo);
+    if (rc) { free_out (mo[0]); return rc; }
+    fill_result (out, mo[0], k, countonly != 0);
+    return 0;
+  }
+  // left chain ((L0 ^ L1) ^ L2) ...: exactly the reference's in-order fold (:668-677), including
+  // the "!freq ||" guard of rule min; only the last link applies the cut-off (:682)
+  DevList acc{lists[0]->words, lists[0]->counts, lists[0]->n_words};
+  bool cur_owned = false;
+  for (unsigned j = 1; j < n_lists; j++) {
+    const bool last = (j + 1 == n_lists);
+    MergeOut mo[4];
+    if (last && caller) { mo[0].caller = true; mo[0].words = out->words; mo[0].counts = out->counts; mo[0].capacity = out->capacity; }
+    SetOpParams p = nlist_params (last ? SEM_NISECT_FINAL : SEM_NISECT_PARTIAL, rule, cutoff, count_override);
+    rc = merge2_device (acc, DevList{lists[j]->words, lists[j]->counts, lists[j]->n_words}, p, OP_UNION, last && countonly, mo);
+    if (cur_owned) free_out (cur);
+    if (rc) { free_out (mo[0]); return rc; }
+    cur = mo[0];
+    cur_owned = true;
+    acc = DevList{cur.words, cur.counts, cur.n};
+  }
+  fill_result (out, cur, k, countonly != 0);
+  return 0;
+}
+
+int gt4gpu_write_union (const gt4gpu_list *const *lists, unsigned n_lists, uint32_t cutoff, int ofile, gt4gpu_header *header)
+{
+  // preconditions of src/set-operations.c:49-50
+  if (!lists || !header || n_lists == 0 || n_lists > 4096) return fail (GT4GPU_ERR_ARG, "gt4gpu_write_union: bad arguments");
+  gt4gpu_result res;
+  memset (&res, 0, sizeof (res));
+  int rc = gt4gpu_union_multi (lists, n_lists, cutoff, GT4GPU_RULE_ADD, 0, ofile == 0, &res);
+  if (rc) return rc;
+  gt4gpu_header_init (header, res.word_length);
+  header->n_words = res.n_words;
+  header->total_count = res.total_count;
+  if (ofile) {
+    // header at the current position, records after it, final header at offset 0 (:75,:117-119)
+    rc = write_all (ofile, header, sizeof (*header), -1);
+    if (!rc) rc = download_aos (res.words, res.counts, res.n_words, nullptr,
+                                [&] (const void *p, size_t bytes, uint64_t) { return write_all (ofile, p, bytes, -1); }, true);
+    if (!rc) rc = write_all (ofile, header, sizeof (*header), 0);
+  }
+  gt4gpu_result_free (&res);
+  return rc;
+}
+
+int gt4gpu_union_matrix (const gt4gpu_list *const *lists, unsigned n_lists, int is_union,
+                         uint64_t *words, uint32_t *counts, uint64_t max_rows, uint64_t *n_rows)
+{
+  if (!lists || !n_rows || n_lists == 0 || n_lists > 4096) return fail (GT4GPU_ERR_ARG, "gt4gpu_union_matrix: bad arguments");
+  for (unsigned j = 0; j < n_lists; j++)
+    if (!lists[j] || lists[j]->n_words == 0) return fail (GT4GPU_ERR_ARG, "gt4gpu_union_matrix: list %u is empty (undefined in the reference)", j);
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  // row keys: list 0 (is_union) or the N-list union with nothing filtered
+  gt4gpu_result rows;
+  memset (&rows, 0, sizeof (rows));
+  const uint64_t *d_rows;
+  uint64_t n;
+  if (is_union) {
+    d_rows = lists[0]->words;
+    n = lists[0]->n_words;
+  } else {
+    rc = gt4gpu_union_multi (lists, n_lists, 0, GT4GPU_RULE_MAX, 0, 0, &rows);   // max never wraps: every key survives cutoff 0
+    if (rc) return rc;
+    d_rows = rows.words;
+    n = rows.n_words;
+  }
+  uint32_t *d_matrix = nullptr;
+  rc = dev_alloc ((void **) &d_matrix, n * n_lists * sizeof (uint32_t));
+  if (rc) { gt4gpu_result_free (&rows); return rc; }
+  cudaError_t e = cudaMemsetAsync (d_matrix, 0, n * n_lists * sizeof (uint32_t), g_ctx.stream);
+  for (unsigned j = 0; j < n_lists && e == cudaSuccess; j++)
+    e = launch_scatter_counts (d_rows, n, lists[j]->words, lists[j]->counts, lists[j]->n_words, j, n_lists, d_matrix, g_ctx.stream);
+  std::vector<uint64_t> h_rows (n);
+  std::vector<uint32_t> h_mat (n * n_lists);
+  if (e == cudaSuccess) e = cudaMemcpyAsync (h_rows.data (), d_rows, n * sizeof (uint64_t), cudaMemcpyDeviceToHost, g_ctx.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync (h_mat.data (), d_matrix, n * n_lists * sizeof (uint32_t), cudaMemcpyDeviceToHost, g_ctx.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.stream);
+  dev_free (d_matrix);
+  gt4gpu_result_free (&rows);
+  if (e != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "gt4gpu_union_matrix: %s", cudaGetErrorString (e));
+
+  // gt4_union revisits the stale last word of a list that runs out while others are still live
+  // and calls back once more with all-zero counts (src/set-operations.c:159-172); reproduce
+  // those rows: one after each word that ends some list, unless it is the overall last word.
+  std::vector<uint64_t> last_words;
+  if (!is_union) {
+    std::vector<uint64_t> tmp (1);
+    for (unsigned j = 0; j < n_lists; j++) {
+      cudaMemcpy (tmp.data (), lists[j]->words + lists[j]->n_words - 1, sizeof (uint64_t), cudaMemcpyDeviceToHost);
+      last_words.push_back (tmp[0]);
+    }
+    std::sort (last_words.begin (), last_words.end ());
+    last_words.erase (std::unique (last_words.begin (), last_words.end ()), last_words.end ());
+  }
+  uint64_t r = 0;
+  size_t lw = 0;
+  auto put = [&] (uint64_t w, const uint32_t *c) {
+    if (r < max_rows && words && counts) {
+      words[r] = w;
+      for (unsigned j = 0; j < n_lists; j++) counts[r * n_lists + j] = c ? c[j] : 0u;
+    }
+    r += 1;
+  };
+  for (uint64_t i = 0; i < n; i++) {
+    put (h_rows[i], &h_mat[i * n_lists]);
+    if (!is_union) {
+      while (lw < last_words.size () && last_words[lw] < h_rows[i]) lw++;
+      if (lw < last_words.size () && last_words[lw] == h_rows[i] && i + 1 < n) put (h_rows[i], nullptr);
+    }
+  }
+  *n_rows = r;
+  return 0;
+}
+
+// ------------------------------------------------------------------ results
+
+int gt4gpu_result_to_host_soa (const gt4gpu_result *res, uint64_t *words, uint32_t *counts)
+{
+  if (!res) return fail (GT4GPU_ERR_ARG, "null argument");
+  if (res->flags & GT4GPU_RESULT_COUNT_ONLY) return fail (GT4GPU_ERR_ARG, "count-only result holds no records");
+  if (res->n_words == 0) return 0;
+  if (!words || !counts) return fail (GT4GPU_ERR_ARG, "null argument");
+  CU (cudaMemcpyAsync (words, res->words, res->n_words * sizeof (uint64_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+  CU (cudaMemcpyAsync (counts, res->counts, res->n_words * sizeof (uint32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+  CU (cudaStreamSynchronize (g_ctx.stream));
+  return 0;
+}
+
+int gt4gpu_result_to_host_aos (const gt4gpu_result *res, void *records)
+{
+  if (!res) return fail (GT4GPU_ERR_ARG, "null argument");
+  if (res->flags & GT4GPU_RESULT_COUNT_ONLY) return fail (GT4GPU_ERR_ARG, "count-only result holds no records");
+  if (res->n_words == 0) return 0;
+  if (!records) return fail (GT4GPU_ERR_ARG, "null argument");
+  return download_aos (res->words, res->counts, res->n_words, records, [] (const void *, size_t, uint64_t) { return 0; }, false);
+}
+
+int gt4gpu_write_records_at (const gt4gpu_result *res, int fd, uint64_t first_record)
+{
+  if (!res || fd < 0) return fail (GT4GPU_ERR_ARG, "bad argument");
+  if (res->flags & GT4GPU_RESULT_COUNT_ONLY) return fail (GT4GPU_ERR_ARG, "count-only result holds no records");
+  const int64_t base = (int64_t) (sizeof (gt4gpu_header) + 12ull * first_record);
+  return download_aos (res->words, res->counts, res->n_words, nullptr,
+                       [&] (const void *p, size_t bytes, uint64_t first) { return write_all (fd, p, bytes, base + (int64_t) (first * 12)); }, true);
+}
+
+int gt4gpu_write_list (const gt4gpu_result *res, int fd)
+{
+  if (!res || fd < 0) return fail (GT4GPU_ERR_ARG, "bad argument");
+  gt4gpu_header h;
+  gt4gpu_header_init (&h, res->word_length);
+  h.n_words = res->n_words;
+  h.total_count = res->total_count;
+  int rc = write_all (fd, &h, sizeof (h), 0);
+  if (rc) return rc;
+  return gt4gpu_write_records_at (res, fd, 0);
+}
+
+void gt4gpu_result_free (gt4gpu_result *res)
+{
+  if (!res) return;
+  if (!(res->flags & GT4GPU_RESULT_CALLER_BUFFERS)) {
+    dev_free (res->words);
+    dev_free (res->counts);
+  }
+  res->words = nullptr;
+  res->counts = nullptr;
+  res->capacity = 0;
+}
+
+// ------------------------------------------------------------------ host-to-host
+
+int gt4gpu_compare2_host_aos (const void *records_a, uint64_t n_a, const void *records_b, uint64_t n_b,
+                              uint32_t word_length, uint32_t ops, int rule, uint32_t cutoff,
+                              uint32_t count_override, int subtract, int countonly,
+                              void *const out_records[4], const uint64_t out_capacity[4],
+                              uint64_t n_out[4], uint64_t total_out[4])
+{
+  if (!n_out || !total_out) return fail (GT4GPU_ERR_ARG, "null argument");
+  gt4gpu_list *a = nullptr, *b = nullptr;
+  int rc = gt4gpu_list_from_host_aos (records_a, n_a, word_length, &a);
+  if (!rc) rc = gt4gpu_list_from_host_aos (records_b, n_b, word_length, &b);
+  gt4gpu_result res[4];
+  memset (res, 0, sizeof (res));
+  if (!rc) rc = gt4gpu_compare2 (a, b, ops, rule, cutoff, count_override, subtract, countonly, res);
+  float ms_p = tl_ms_partition, ms_m = tl_ms_merge;
+  uint32_t nl = tl_launches;
+  for (int s = 0; s < 4 && !rc; s++) {
+    if (!((ops >> s) & 1u)) continue;
+    n_out[s] = res[s].n_words;
+    total_out[s] = res[s].total_count;
+    if (countonly) continue;
+    if (!out_records || !out_capacity || (res[s].n_words && !out_records[s])) rc = fail (GT4GPU_ERR_ARG, "missing output buffer for stream %d", s);
+    else if (res[s].n_words > out_capacity[s]) rc = fail (GT4GPU_ERR_CAPACITY, "stream %d needs %llu records", s, (unsigned long long) res[s].n_words);
+    else rc = gt4gpu_result_to_host_aos (&res[s], out_records[s]);
+  }
+  for (int s = 0; s < 4; s++) gt4gpu_result_free (&res[s]);
+  gt4gpu_list_close (a);
+  gt4gpu_list_close (b);
+  tl_ms_partition = ms_p; tl_ms_merge = ms_m; tl_launches = nl;
+  return rc;
+}
+
+// ------------------------------------------------------------------ sharding plan (host only)
+
+int gt4gpu_plan_splitters (const void *const *keys, const size_t *stride_bytes, const uint64_t *n_words,
+                           unsigned n_lists, unsigned n_parts, uint64_t *bounds, uint64_t *splitters)
+{
+  if (!keys || !stride_bytes || !n_words || !bounds || n_lists == 0 || n_parts == 0) return fail (GT4GPU_ERR_ARG, "bad argument");
+  auto key_at = [&] (unsigned j, uint64_t i) {
+    uint64_t v;
+    memcpy (&v, static_cast<const unsigned char *> (keys[j]) + i * stride_bytes[j], sizeof (v));
+    return v;
+  };
+  // number of records of list j with key < K
+  auto below = [&] (unsigned j, uint64_t K) {
+    uint64_t lo = 0, hi = n_words[j];
+    while (lo < hi) {
+      const uint64_t mid = lo + ((hi - lo) >> 1);
+      if (key_at (j, mid) < K) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  };
+  uint64_t total = 0;
+  for (unsigned j = 0; j < n_lists; j++) total += n_words[j];
+  const unsigned stride = n_parts + 1;
+  for (unsigned j = 0; j < n_lists; j++) {
+    bounds[j * stride] = 0;
+    bounds[j * stride + n_parts] = n_words[j];
+  }
+  for (unsigned p = 1; p < n_parts; p++) {
+    // exact co-rank on key VALUES: the smallest K with  sum_j |{x in L_j : x < K}| >= target
+    const uint64_t target = (uint64_t) (((unsigned __int128) total * p) / n_parts);
+    uint64_t lo = 0, hi = UINT64_MAX;
+    while (lo < hi) {
+      const uint64_t mid = lo + ((hi - lo) >> 1);
+      uint64_t cnt = 0;
+      for (unsigned j = 0; j < n_lists; j++) cnt += below (j, mid);
+      if (cnt >= target) hi = mid;
+      else lo = mid + 1;
+    }
+    if (splitters) splitters[p - 1] = lo;
+    for (unsigned j = 0; j < n_lists; j++) bounds[j * stride + p] = below (j, lo);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ helpers for harnesses
+
+int gt4gpu_deinterleave (const void *d_records, uint64_t n, uint64_t *d_words, uint32_t *d_counts)
+{
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  CU (launch_deinterleave (d_records, n, d_words, d_counts, g_ctx.stream));
+  CU (cudaStreamSynchronize (g_ctx.stream));
+  return 0;
+}
+
+int gt4gpu_interleave (const uint64_t *d_words, const uint32_t *d_counts, uint64_t n, void *d_records)
+{
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  CU (launch_interleave (d_words, d_counts, n, d_records, g_ctx.stream));
+  CU (cudaStreamSynchronize (g_ctx.stream));
+  return 0;
+}
+
+}  // extern "C"

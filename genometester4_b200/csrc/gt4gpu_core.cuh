@@ -1,0 +1,184 @@
+// gt4gpu_core.cuh -- arithmetic shared by every kernel of the engine: the count
+// rules, the per-output predicates, the merge-path co-rank search and the
+// per-thread serial merge.  Everything here is integer-only and
+// __host__ __device__, so the unit tests can drive exactly the code the
+// kernels run (tests/emulate_tile.cpp) without a GPU.
+//
+// Semantics follow /root/reference/src/glistcompare.c:433-489 (rules and
+// predicates), :843-905 (two-list loop), :545-591 / :647-705 (N-list loops).
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GT4_HD __host__ __device__ __forceinline__
+#define GT4_UNROLL _Pragma ("unroll")
+#else
+#define GT4_HD inline
+#define GT4_UNROLL
+#endif
+
+namespace gt4gpu {
+
+enum Rule : int {
+  RULE_DEFAULT = 0, RULE_ADD = 1, RULE_SUBTRACT = 2, RULE_MIN = 3, RULE_MAX = 4,
+  RULE_FIRST = 5, RULE_SECOND = 6, RULE_NUMBER = 7
+};
+
+enum : uint32_t { OP_UNION = 1u, OP_INTRSEC = 2u, OP_DIFF = 4u, OP_DDIFF = 8u };
+
+// How a merged key's (f1, f2) pair is turned into output records.
+enum Semantics : int {
+  SEM_PAIR = 0,            // compare_wordmaps: up to 4 streams, "!= 0" filter, cutoff on the inputs
+  SEM_NUNION_PARTIAL = 1,  // inner node of an N-list union: combine, keep everything
+  SEM_NUNION_FINAL = 2,    // last node of an N-list union: combine, keep iff combined >= cutoff
+  SEM_NISECT_PARTIAL = 3,  // inner node of an N-list intersection chain
+  SEM_NISECT_FINAL = 4
+};
+
+struct SetOpParams {
+  uint32_t ops;             // requested streams (SEM_PAIR); N-list semantics use stream 0 only
+  uint32_t cutoff;
+  uint32_t count_override;  // RULE_NUMBER value (glistcompare.c:82)
+  int rule[4];              // resolved rule per stream (RULE_DEFAULT already substituted)
+  int subtract;             // -du
+  int sem;
+};
+
+// calculate_freq, glistcompare.c:433-455
+GT4_HD uint32_t calc_freq (uint32_t f1, uint32_t f2, int rule, uint32_t ov)
+{
+  switch (rule) {
+  case RULE_ADD:      return f1 + f2;
+  case RULE_SUBTRACT: return (f1 > f2) ? f1 - f2 : 0u;
+  case RULE_MIN:      return (f1 < f2) ? f1 : f2;
+  case RULE_MAX:      return (f1 > f2) ? f1 : f2;
+  case RULE_FIRST:    return f1;
+  case RULE_SECOND:   return f2;
+  case RULE_NUMBER:   return ov;
+  default:            return 0u;
+  }
+}
+
+// Resolve RULE_DEFAULT per stream the way include_in_* do (glistcompare.c:462,471,485).
+GT4_HD int resolve_rule (int rule, int stream)
+{
+  if (rule != RULE_DEFAULT) return rule;
+  return stream == 0 ? RULE_ADD : stream == 1 ? RULE_MIN : RULE_SUBTRACT;
+}
+
+// One merged key -> does stream `s` emit it, and with which count?
+// c1/c2 are the stored counts, in_a/in_b say which lists hold the key; an absent side
+// contributes 0 exactly as the reference passes a literal 0 (glistcompare.c:875,880,891,896).
+GT4_HD bool eval_stream (const SetOpParams &p, int s, uint32_t c1, uint32_t c2, bool in_a, bool in_b, uint32_t &f)
+{
+  const uint32_t f1 = in_a ? c1 : 0u;
+  const uint32_t f2 = in_b ? c2 : 0u;
+  const uint32_t c = p.cutoff;
+  if (p.sem == SEM_PAIR) {
+    switch (s) {
+    case 0:   // include_in_union, :459-466
+      if (f1 < c && f2 < c) return false;
+      f = calc_freq (f1, f2, p.rule[0], p.count_override);
+      return f != 0u;
+    case 1:   // include_in_intersection, :468-475 (only reached for keys in both lists, :852)
+      if (!(in_a && in_b)) return false;
+      if (f1 < c || f2 < c) return false;
+      f = calc_freq (f1, f2, p.rule[1], p.count_override);
+      return f != 0u;
+    case 2:   // include_in_complement (list 1 minus list 2), :477-489
+      if (!in_a) return false;
+      if (p.subtract) {
+        if (f1 != f2 || f1 < c) return false;
+        f = f1;
+        return true;
+      }
+      if (f1 < c || f2 >= c) return false;
+      f = calc_freq (f1, f2, p.rule[2], p.count_override);
+      return f != 0u;
+    default:  // diff2: arguments swapped, subtract forced to 0 (:862,:896)
+      if (!in_b) return false;
+      if (f2 < c || f1 >= c) return false;
+      f = calc_freq (f2, f1, p.rule[3], p.count_override);
+      return f != 0u;
+    }
+  }
+  if (s != 0) return false;
+  const int rule = p.rule[0];
+  if (p.sem == SEM_NUNION_PARTIAL || p.sem == SEM_NUNION_FINAL) {
+    // union_multi, :549-557: fold of the counts of the lists holding the key (0 is neutral for
+    // add and max, so the absent side needs no special case); emit iff combined >= cutoff (:574)
+    if (rule == RULE_ADD) f = f1 + f2;
+    else if (rule == RULE_MAX) f = (f1 > f2) ? f1 : f2;
+    else f = p.count_override;
+    return p.sem == SEM_NUNION_PARTIAL ? true : f >= c;
+  }
+  // intersect_multi, :668-677: left fold over the lists in order; f1 is the fold so far
+  if (!(in_a && in_b)) return false;
+  if (rule == RULE_MIN) f = (f1 == 0u || f2 < f1) ? f2 : f1;     // the "!freq ||" guard of :669
+  else if (rule == RULE_MAX) f = (f2 > f1) ? f2 : f1;
+  else if (rule == RULE_ADD) f = f1 + f2;
+  else f = p.count_override;
+  return p.sem == SEM_NISECT_PARTIAL ? true : f >= c;
+}
+
+// Merge-path co-rank: how many elements of A are among the first `diag` elements of the merge
+// of A and B when ties take A first.  Works on any random-access key arrays (global or shared).
+template <typename Index>
+GT4_HD Index merge_path (const uint64_t *a, Index na, const uint64_t *b, Index nb, Index diag)
+{
+  Index lo = diag > nb ? diag - nb : 0;
+  Index hi = diag < na ? diag : na;
+  while (lo < hi) {
+    const Index mid = lo + ((hi - lo) >> 1);
+    if (a[mid] <= b[diag - 1 - mid]) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// One thread's share of a tile: VT consecutive slots of the merged sequence starting at slot
+// `d0`, A-cursor `i0` (= merge_path (..., d0)).  ka/ca and kb/cb are the tile's slices; ka[-1] is
+// readable iff has_halo (the element of A just before the tile) and kb[nb] iff has_peek (the
+// element of B just after it).  Every distinct key is reported exactly once:
+//   - an A slot always reports, pairing with the next unconsumed B element when equal;
+//   - a B slot reports unless the A element just before it carries the same key (then the A
+//     slot -- possibly in the previous thread or tile -- already reported the pair).
+// sink (slot, key, c1, c2, in_a, in_b, live) is called for all VT slots; live == false marks
+// slots past the end of the tile or the second half of a pair.
+template <int VT, typename Sink>
+GT4_HD void merge_slots (const uint64_t *ka, const uint32_t *ca, int na, bool has_halo,
+                         const uint64_t *kb, const uint32_t *cb, int nb, bool has_peek,
+                         int i0, int d0, Sink &&sink)
+{
+  const int n_tile = na + nb;
+  const int nb_ext = nb + (has_peek ? 1 : 0);
+  int i = i0, j = d0 - i0;
+  bool prev_ok = (i0 > 0) || has_halo;
+  uint64_t prev_a = prev_ok ? ka[i - 1] : 0ull;
+  uint64_t key_a = ka[i];     // may be past the slice: the buffers carry slack, value unused then
+  uint64_t key_b = kb[j];
+GT4_UNROLL
+  for (int s = 0; s < VT; s++) {
+    const bool a_avail = i < na;
+    const bool b_avail = j < nb;
+    const bool take_a = a_avail && (!b_avail || key_a <= key_b);
+    const uint32_t cnt_a = ca[i];
+    const uint32_t cnt_b = cb[j];
+    const bool pair = take_a && (j < nb_ext) && (key_b == key_a);
+    const bool dup_b = !take_a && prev_ok && (prev_a == key_b);
+    const bool live = (d0 + s < n_tile) && !dup_b;
+    sink (s, take_a ? key_a : key_b, cnt_a, cnt_b, take_a, !take_a || pair, live);
+    if (take_a) {
+      prev_a = key_a;
+      prev_ok = true;
+      i += 1;
+      key_a = ka[i];
+    } else {
+      j += 1;
+      key_b = kb[j];
+    }
+  }
+}
+
+}  // namespace gt4gpu

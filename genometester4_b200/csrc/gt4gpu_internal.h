@@ -1,0 +1,63 @@
+// gt4gpu_internal.h -- launch interface between the C-ABI layer (gt4gpu_api.cu)
+// and the sm_100a kernels (gt4gpu_kernels.cu).  Not installed; not part of the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gt4gpu_core.cuh"
+
+namespace gt4gpu {
+
+// Per-call scratch living in HBM, zeroed before every launch.
+//   [0]      u32 ticket       -- dynamic tile counter (tiles are claimed in launch order so the
+//                                decoupled look-back never waits on a tile that has not started)
+//   [1]      u32 overflow     -- set when a caller-provided output buffer is too small
+//   [2..]    u64 totals[4][TOTAL_SLOTS][2] -- per stream: records emitted, sum of emitted counts,
+//                                spread over TOTAL_SLOTS addresses (tile % TOTAL_SLOTS) so the
+//                                per-tile reductions do not serialise on one L2 atomic unit;
+//                                the host adds the slots up
+static constexpr int TOTAL_SLOTS = 64;
+struct CallHeader {
+  uint32_t ticket;
+  uint32_t overflow;
+  unsigned long long totals[4][TOTAL_SLOTS][2];
+};
+
+struct TileArgs {
+  const uint64_t *a_words;
+  const uint32_t *a_counts;
+  uint64_t na;
+  const uint64_t *b_words;
+  const uint32_t *b_counts;
+  uint64_t nb;
+  const uint64_t *part;        // n_tiles + 1 co-ranks: A index at diagonal t * TILE
+  uint64_t n_tiles;
+  uint64_t *out_words[4];
+  uint32_t *out_counts[4];
+  uint64_t out_capacity[4];
+  CallHeader *hdr;
+  uint64_t *desc;              // look-back descriptors, [stream slot][n_tiles]
+  int stream0;                 // the single requested stream when the 1-stream kernel is used
+  SetOpParams p;
+};
+
+struct TileShape { int threads, items; };
+
+bool tile_shape_supported (int threads, int items);
+size_t tile_smem_bytes (int threads, int items);
+
+// co-rank of every tile boundary
+cudaError_t launch_partition (const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb,
+                              uint32_t tile, uint64_t n_tiles, uint64_t *part, cudaStream_t st);
+// the merge itself; n_streams is 1 or 4 (4 = fused multi-output pass)
+cudaError_t launch_setop2 (const TileArgs &args, TileShape shape, int n_streams, bool count_only, cudaStream_t st);
+
+cudaError_t launch_deinterleave (const void *records, uint64_t n, uint64_t *words, uint32_t *counts, cudaStream_t st);
+cudaError_t launch_interleave (const uint64_t *words, const uint32_t *counts, uint64_t n, void *records, cudaStream_t st);
+
+// counts[row(words_j[i]) * n_lists + j] = counts_j[i], rows found by binary search in `rows`
+cudaError_t launch_scatter_counts (const uint64_t *rows, uint64_t n_rows, const uint64_t *words, const uint32_t *counts,
+                                   uint64_t n, unsigned j, unsigned n_lists, uint32_t *matrix, cudaStream_t st);
+
+}  // namespace gt4gpu
