@@ -49,7 +49,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=1e8, help="k-mers per list of the CPU baseline sample")
     ap.add_argument("--ref-sample", type=float, default=4e7, help="k-mers per list per step of --impl reference")
-    ap.add_argument("--tile", type=str, default=None, help="e.g. 256x9")
+    ap.add_argument("--tile", type=str, default=None, help="multi-output kernel tile, e.g. 256x9")
+    ap.add_argument("--stream-items", type=int, default=None, help="items per thread of the single-output kernel (7/9/11/13)")
+    ap.add_argument("--no-stream-kernel", action="store_true", help="route the merge through setop2_tile_kernel")
     return ap.parse_args()
 
 
@@ -76,15 +78,17 @@ def ncu_traffic():
     p = ROOT / "profiles" / "ncu_summary.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get("setop2_tile_kernel", {}).get("dram_bytes_per_launch")
+            return json.loads(p.read_text()).get("setop2_stream_kernel", {}).get("dram_bytes_per_launch")
         except Exception:
             return None
     return None
 
 
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi sampled every 100 ms from before the warm-up; only samples whose timestamp falls inside
+    the timed region count (the recipe's clocks line, /opt/skills/guides/B200_PROFILING.md)."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.path = index, None, None
@@ -98,31 +102,43 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        inside, everything, smax, reasons, power = [], [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in Path(self.path).read_text().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                sm = float(f[1])
+                smax = float(f[2])
             except ValueError:
                 continue
-            for nme, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nme)
+            everything.append(sm)
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                inside.append(sm)
+                try:
+                    power.append(float(f[3]))
+                except ValueError:
+                    pass
+                for nme, val in zip(names, f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
         os.unlink(self.path)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        use = inside if inside else everything
+        return {"sm_mhz": statistics.median(use) if use else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples_in_timed_region": len(inside), "samples": len(everything),
+                "power_w_max": max(power) if power else None}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -252,6 +268,10 @@ def run_gt4gpu_arm(args):
     if args.tile:
         nt, vt = args.tile.split("x")
         g.set_tile(int(nt), int(vt))
+    if args.stream_items:
+        g.set_option("stream_items", args.stream_items)
+    if args.no_stream_kernel:
+        g.set_option("use_stream_kernel", 0)
     g.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # ---- this rank's shard of the synthetic lists, generated in HBM
@@ -285,16 +305,16 @@ def run_gt4gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        res = step()
-    n_out = res.n_words
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    n_out = res.n_words
     part_ms, merge_ms, launches = [], [], 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
@@ -304,7 +324,8 @@ def run_gt4gpu_arm(args):
         launches += nl
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_step = ev0.elapsed_time(ev1) / args.steps
     stats = torch.tensor([ms_step, statistics.mean(merge_ms), statistics.mean(part_ms)], dtype=torch.float64, device="cuda")
     sizes = torch.tensor([na + nb, n_out], dtype=torch.int64, device="cuda")
@@ -319,7 +340,8 @@ def run_gt4gpu_arm(args):
     peak, peak_src = peaks()
     algo_bytes = 12 * (na + nb) + (0 if args.count_only else 12 * n_out)
     achieved = algo_bytes / (statistics.mean(merge_ms) / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "setop2_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kernel_name = "setop2_tile_kernel" if args.no_stream_kernel else "setop2_stream_kernel"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": statistics.mean(merge_ms),
                 "partition_kernel_ms": statistics.mean(part_ms),
@@ -343,7 +365,8 @@ def run_gt4gpu_arm(args):
                 "dtype": "u64 keys / u32 counts (integer compare, add mod 2^32)", "data": "synthetic",
                 "config": workload_config(args, na, nb), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks,
-                "output_kmers": total_out, "input_kmers": total_in, "tile": args.tile or os.environ.get("GT4GPU_TILE", "256x9")}
+                "output_kmers": total_out, "input_kmers": total_in, "kernel_config": {"kernel": kernel_name, "stream_items": args.stream_items or int(os.environ.get("GT4GPU_STREAM_ITEMS", "9")),
+                                  "tile": args.tile or os.environ.get("GT4GPU_TILE", "256x9")}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -47,6 +47,7 @@ SIGNATURES = {
     "gt4gpu_set_stream": (_I, [_P]),
     "gt4gpu_last_error": (C.c_char_p, []),
     "gt4gpu_set_tile": (_I, [_I, _I]),
+    "gt4gpu_set_option": (_I, [C.c_char_p, _I]),
     "gt4gpu_last_timing": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_U32)]),
     "gt4gpu_list_open": (_I, [C.c_char_p, _I, C.POINTER(_P)]),
     "gt4gpu_list_open_range": (_I, [C.c_char_p, _I, _U64, _U64, C.POINTER(_P)]),

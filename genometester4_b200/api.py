@@ -58,6 +58,11 @@ def set_tile(threads: int, items: int) -> None:
     _check(_lib.load().gt4gpu_set_tile(threads, items))
 
 
+def set_option(name: str, value: int) -> None:
+    """Tuning knobs of the library: "stream_items" (7/9/11/13), "use_stream_kernel" (0/1)."""
+    _check(_lib.load().gt4gpu_set_option(name.encode(), int(value)))
+
+
 def last_timing():
     """(partition_ms, merge_ms, launches) of the most recent merge call, from CUDA events."""
     a, b, n = C.c_float(), C.c_float(), C.c_uint32()

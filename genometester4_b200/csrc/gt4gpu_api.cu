@@ -45,7 +45,10 @@ struct Context {
   int device = -1;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  TileShape shape = {256, 9};
+  TileShape shape = {256, 9};   // tile shape of the multi-output kernel (setop2_tile_kernel)
+  int stream_items = 9;         // items per thread of the single-output kernel (setop2_stream_kernel)
+  int use_stream = 1;           // 0: run single-output merges through setop2_tile_kernel too
+  int sm_count = 0;
 };
 Context g_ctx;
 
@@ -122,7 +125,8 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   if (n_req == 0) return fail (GT4GPU_ERR_ARG, "no output stream requested");
   const int ns = (n_req == 1) ? 1 : 4;
   const TileShape shape = g_ctx.shape;
-  const uint64_t tile = (uint64_t) shape.threads * shape.items;
+  const bool use_stream = (n_req == 1) && g_ctx.use_stream;
+  const uint64_t tile = use_stream ? (uint64_t) stream_tile_size (g_ctx.stream_items) : (uint64_t) shape.threads * shape.items;
   const uint64_t n_tiles = (total + tile - 1) / tile;
   cudaStream_t st = g_ctx.stream;
 
@@ -171,7 +175,8 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   CU (cudaEventRecord (tl_ev[0], st));
   CU (launch_partition (a.words, a.n, b.words, b.n, (uint32_t) tile, n_tiles, part, st));
   CU (cudaEventRecord (tl_ev[1], st));
-  CU (launch_setop2 (args, shape, ns, countonly, st));
+  if (use_stream) CU (launch_setop2_stream (args, g_ctx.stream_items, countonly, g_ctx.sm_count, st));
+  else CU (launch_setop2 (args, shape, ns, countonly, st));
   CU (cudaEventRecord (tl_ev[2], st));
 
   CallHeader h;
@@ -463,7 +468,15 @@ int gt4gpu_init (int device)
   CU (cudaDeviceGetDefaultMemPool (&pool, g_ctx.device));
   uint64_t keep = UINT64_MAX;
   CU (cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  const char *env = getenv ("GT4GPU_TILE");   // e.g. GT4GPU_TILE=256x11
+  CU (cudaDeviceGetAttribute (&g_ctx.sm_count, cudaDevAttrMultiProcessorCount, g_ctx.device));
+  const char *env = getenv ("GT4GPU_STREAM_ITEMS");   // items per thread of the single-output kernel
+  if (env) {
+    if (!stream_shape_supported (atoi (env))) return fail (GT4GPU_ERR_ARG, "GT4GPU_STREAM_ITEMS=%s is not supported", env);
+    g_ctx.stream_items = atoi (env);
+  }
+  env = getenv ("GT4GPU_USE_STREAM_KERNEL");
+  if (env) g_ctx.use_stream = atoi (env) != 0;
+  env = getenv ("GT4GPU_TILE");   // multi-output kernel, e.g. GT4GPU_TILE=256x11
   if (env) {
     int nt = 0, vt = 0;
     if (sscanf (env, "%dx%d", &nt, &vt) == 2 && tile_shape_supported (nt, vt)) g_ctx.shape = TileShape{nt, vt};
@@ -497,6 +510,21 @@ int gt4gpu_set_tile (int threads, int items_per_thread)
     return fail (GT4GPU_ERR_ARG, "unsupported tile shape %dx%d", threads, items_per_thread);
   g_ctx.shape = TileShape{threads, items_per_thread};
   return 0;
+}
+
+int gt4gpu_set_option (const char *name, int value)
+{
+  if (!name) return fail (GT4GPU_ERR_ARG, "null option name");
+  if (!strcmp (name, "stream_items")) {
+    if (!stream_shape_supported (value)) return fail (GT4GPU_ERR_ARG, "stream_items=%d is not supported", value);
+    g_ctx.stream_items = value;
+    return 0;
+  }
+  if (!strcmp (name, "use_stream_kernel")) {
+    g_ctx.use_stream = value != 0;
+    return 0;
+  }
+  return fail (GT4GPU_ERR_ARG, "unknown option %s", name);
 }
 
 int gt4gpu_last_timing (float *ms_partition, float *ms_merge, uint32_t *n_launches)

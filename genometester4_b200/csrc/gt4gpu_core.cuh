@@ -122,6 +122,59 @@ GT4_HD bool eval_stream (const SetOpParams &p, int s, uint32_t c1, uint32_t c2, 
   return p.sem == SEM_NISECT_PARTIAL ? true : f >= c;
 }
 
+// Compile-time specialisations of eval_stream for the single-output configurations that matter
+// for throughput (the defaults of glistcompare and the nodes of the N-list tree / chain).  Each
+// must agree with eval_stream for the parameters it is selected for (select_fast_path);
+// tests/test_core_emulation.py checks that exhaustively on random inputs.
+enum FastPath : int {
+  FAST_GENERIC = 0,   // runtime eval_stream
+  FAST_U_ADD = 1,     // SEM_PAIR, union, rule add
+  FAST_I_MIN = 2,     // SEM_PAIR, intersection, rule min
+  FAST_D_SUB = 3,     // SEM_PAIR, diff1, rule subtract, no -du
+  FAST_NU_ADD = 4,    // N-list union node, rule add
+  FAST_NI_MIN = 5     // N-list intersection link, rule min
+};
+
+GT4_HD int select_fast_path (const SetOpParams &p, int stream)
+{
+  if (p.sem == SEM_PAIR) {
+    if (stream == 0 && p.rule[0] == RULE_ADD) return FAST_U_ADD;
+    if (stream == 1 && p.rule[1] == RULE_MIN) return FAST_I_MIN;
+    if (stream == 2 && p.rule[2] == RULE_SUBTRACT && !p.subtract) return FAST_D_SUB;
+    return FAST_GENERIC;
+  }
+  if (stream != 0) return FAST_GENERIC;
+  if ((p.sem == SEM_NUNION_PARTIAL || p.sem == SEM_NUNION_FINAL) && p.rule[0] == RULE_ADD) return FAST_NU_ADD;
+  if ((p.sem == SEM_NISECT_PARTIAL || p.sem == SEM_NISECT_FINAL) && p.rule[0] == RULE_MIN) return FAST_NI_MIN;
+  return FAST_GENERIC;
+}
+
+template <int FAST>
+GT4_HD bool eval_fast (const SetOpParams &p, int stream, uint32_t c1, uint32_t c2, bool in_a, bool in_b, uint32_t &f)
+{
+  const uint32_t c = p.cutoff;
+  if (FAST == FAST_U_ADD) {
+    const uint32_t f1 = in_a ? c1 : 0u, f2 = in_b ? c2 : 0u;
+    f = f1 + f2;
+    return (f1 >= c || f2 >= c) && f != 0u;
+  } else if (FAST == FAST_I_MIN) {
+    f = (c1 < c2) ? c1 : c2;
+    return in_a && in_b && f >= c && f != 0u;        // min (c1, c2) >= c  <=>  both >= c
+  } else if (FAST == FAST_D_SUB) {
+    const uint32_t f2 = in_b ? c2 : 0u;
+    f = (c1 > f2) ? c1 - f2 : 0u;
+    return in_a && c1 >= c && f2 < c && f != 0u;
+  } else if (FAST == FAST_NU_ADD) {
+    f = (in_a ? c1 : 0u) + (in_b ? c2 : 0u);
+    return p.sem == SEM_NUNION_PARTIAL || f >= c;
+  } else if (FAST == FAST_NI_MIN) {
+    f = (c1 == 0u || c2 < c1) ? c2 : c1;
+    return in_a && in_b && (p.sem == SEM_NISECT_PARTIAL || f >= c);
+  } else {
+    return eval_stream (p, stream, c1, c2, in_a, in_b, f);
+  }
+}
+
 // Merge-path co-rank: how many elements of A are among the first `diag` elements of the merge
 // of A and B when ties take A first.  Works on any random-access key arrays (global or shared).
 template <typename Index>

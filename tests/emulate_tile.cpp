@@ -82,3 +82,45 @@ extern "C" int emu_setop2 (const uint64_t *aw, const uint32_t *ac, uint64_t na, 
   default: return 1;
   }
 }
+
+// eval_fast<F> must agree with eval_stream wherever select_fast_path picks F.  Returns the number of
+// disagreements over a grid of small and extreme values (0 = pass).
+template <int F>
+static uint64_t check_fast (const SetOpParams &p, int stream)
+{
+  static const uint32_t vals[] = {0u, 1u, 2u, 3u, 4u, 5u, 6u, 100u, 0x7fffffffu, 0x80000000u, 0x80000001u, 0xfffffffeu, 0xffffffffu};
+  uint64_t bad = 0;
+  for (uint32_t c1 : vals) for (uint32_t c2 : vals) for (int ia = 0; ia < 2; ia++) for (int ib = 0; ib < 2; ib++) {
+    if (!ia && !ib) continue;
+    uint32_t f0 = 0, f1 = 0;
+    const bool k0 = eval_stream (p, stream, c1, c2, ia, ib, f0);
+    const bool k1 = eval_fast<F> (p, stream, c1, c2, ia, ib, f1);
+    if (k0 != k1 || (k0 && f0 != f1)) bad++;
+  }
+  return bad;
+}
+
+extern "C" uint64_t emu_check_fast_paths (void)
+{
+  static const uint32_t cutoffs[] = {0u, 1u, 2u, 5u, 100u, 0x80000000u, 0xffffffffu};
+  uint64_t bad = 0, selected[6] = {0, 0, 0, 0, 0, 0};
+  for (int sem = 0; sem < 5; sem++) for (int rule = 0; rule < 8; rule++) for (int sub = 0; sub < 2; sub++)
+    for (uint32_t cutoff : cutoffs) for (int stream = 0; stream < 4; stream++) {
+      SetOpParams p;
+      memset (&p, 0, sizeof (p));
+      p.ops = 1u << stream; p.cutoff = cutoff; p.count_override = 7; p.subtract = sub; p.sem = sem;
+      for (int s = 0; s < 4; s++) p.rule[s] = (sem == SEM_PAIR) ? resolve_rule (rule, s) : (rule == 0 ? 1 : rule);
+      const int f = select_fast_path (p, stream);
+      selected[f]++;
+      switch (f) {
+      case FAST_U_ADD: bad += check_fast<FAST_U_ADD> (p, stream); break;
+      case FAST_I_MIN: bad += check_fast<FAST_I_MIN> (p, stream); break;
+      case FAST_D_SUB: bad += check_fast<FAST_D_SUB> (p, stream); break;
+      case FAST_NU_ADD: bad += check_fast<FAST_NU_ADD> (p, stream); break;
+      case FAST_NI_MIN: bad += check_fast<FAST_NI_MIN> (p, stream); break;
+      default: bad += check_fast<FAST_GENERIC> (p, stream); break;
+      }
+    }
+  for (int f = 1; f < 6; f++) if (!selected[f]) bad += 1000000;   // every fast path must be reachable
+  return bad;
+}

@@ -138,3 +138,8 @@ def test_nlist_tree_and_chain_against_oracle(emu, oracle):
                 assert want.n_words == 0
         n += 1
     assert n > 300
+
+
+def test_fast_path_predicates_agree_with_generic(emu):
+    emu.emu_check_fast_paths.restype = C.c_uint64
+    assert emu.emu_check_fast_paths() == 0

@@ -109,6 +109,85 @@ def test_medium_lists_every_tile_shape(g, oracle, shape):
     g.set_tile(256, 9)
 
 
+@pytest.mark.parametrize("items", [7, 9, 11, 13])
+def test_stream_kernel_every_shape_rule_and_semantics(g, oracle, items):
+    """The persistent single-output kernel (TMA-staged, warp-specialised): every items-per-thread
+    variant x every rule (fast paths and the generic path) x pair / N-list semantics, on inputs of
+    hundreds of tiles with odd sizes so that slices start at every 16-byte misalignment."""
+    g.set_option("stream_items", items)
+    g.set_option("use_stream_kernel", 1)
+    try:
+        for seed, (na, nb, both), kind in ((11, (300_001, 250_003, 120_000), "tail"), (12, (65_537, 65_539, 65_537), "small"),
+                                           (13, (3, 200_001, 2), "tail"), (14, (150_000, 7, 0), "huge"), (15, (5, 3, 2), "tail")):
+            a, b = make_pair(seed, na, nb, both, 25, kind)
+            # sub-views that start at odd element offsets: A[1:], B[3:] are 8- and 12-byte misaligned
+            la, lb = g.WordList.from_arrays(*a, 25), g.WordList.from_arrays(*b, 25)
+            sa, sb = oracle.SList(*a, 25), oracle.SList(*b, 25)
+            for rule in ("default", "add", "subtract", "min", "max", "first", "second", 3):
+                rkw = dict(rule="number", count_override=rule) if isinstance(rule, int) else dict(rule=rule)
+                for cutoff in (1, 3):
+                    want = oracle.compare2(sa, sb, union=True, intrsec=True, diff=True, ddiff=True, cutoff=cutoff, **rkw)
+                    want_du = oracle.compare2(sa, sb, diff=True, subtract=True, cutoff=cutoff, **rkw)["diff1"]
+                    for s, kw in (("union", dict(find_union=1)), ("intrsec", dict(find_intrsec=1)), ("diff1", dict(find_diff=1)),
+                                  ("diff2", dict(find_ddiff=1))):
+                        r = g.compare_wordmaps(la, lb, cutoff=cutoff, **kw, **rkw)[s]
+                        w, c = r.to_host()
+                        assert np.array_equal(w, want[s].words) and np.array_equal(c, want[s].counts), (items, seed, rule, cutoff, s)
+                        assert (r.n_words, r.total_count) == (want[s].n_words, want[s].total_count)
+                        co = g.compare_wordmaps(la, lb, cutoff=cutoff, countonly=1, **kw, **rkw)[s]
+                        assert (co.n_words, co.total_count) == (want[s].n_words, want[s].total_count), (items, seed, rule, cutoff, s, "co")
+                    r = g.compare_wordmaps(la, lb, cutoff=cutoff, find_diff=1, subtract=1, **rkw)["diff1"]
+                    w, c = r.to_host()
+                    assert np.array_equal(w, want_du.words) and np.array_equal(c, want_du.counts), (items, seed, rule, cutoff, "du")
+    finally:
+        g.set_option("stream_items", 9)
+
+
+def test_stream_kernel_misaligned_device_views(g, oracle):
+    """Caller-owned device arrays that start at every 8/4-byte phase of a 16-byte line (the TMA
+    bulk copies over-fetch to 16-byte boundaries and the kernel must shift accordingly)."""
+    import torch
+    a, b = make_pair(31, 40_000, 50_000, 20_000, 25, "tail")
+    for off_a in (0, 1, 2, 3):
+        for off_b in (0, 1, 3):
+            ta = torch.from_numpy(a[0][off_a:].view(np.int64).copy()).cuda()
+            base_w = torch.empty(ta.numel() + 4, dtype=torch.int64, device="cuda")
+            base_c = torch.empty(ta.numel() + 4, dtype=torch.int32, device="cuda")
+            wa = base_w[off_a:off_a + ta.numel()]
+            wa.copy_(ta)
+            ca = base_c[off_a:off_a + ta.numel()]
+            ca.copy_(torch.from_numpy(a[1][off_a:].view(np.int32).copy()).cuda())
+            tb = torch.from_numpy(b[0][off_b:].view(np.int64).copy()).cuda()
+            base_wb = torch.empty(tb.numel() + 4, dtype=torch.int64, device="cuda")
+            base_cb = torch.empty(tb.numel() + 4, dtype=torch.int32, device="cuda")
+            wb = base_wb[off_b:off_b + tb.numel()]
+            wb.copy_(tb)
+            cb = base_cb[off_b:off_b + tb.numel()]
+            cb.copy_(torch.from_numpy(b[1][off_b:].view(np.int32).copy()).cuda())
+            torch.cuda.synchronize()
+            la = g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), wa.numel(), 25, keepalive=(base_w, base_c))
+            lb = g.WordList.from_device(wb.data_ptr(), cb.data_ptr(), wb.numel(), 25, keepalive=(base_wb, base_cb))
+            want = oracle.compare2(oracle.SList(a[0][off_a:], a[1][off_a:], 25), oracle.SList(b[0][off_b:], b[1][off_b:], 25),
+                                   union=True, intrsec=True)
+            for s, kw in (("union", dict(find_union=1)), ("intrsec", dict(find_intrsec=1))):
+                w, c = g.compare_wordmaps(la, lb, **kw)[s].to_host()
+                assert np.array_equal(w, want[s].words) and np.array_equal(c, want[s].counts), (off_a, off_b, s)
+
+
+def test_tile_kernel_still_serves_single_outputs(g, oracle):
+    """use_stream_kernel=0 routes single-output merges through setop2_tile_kernel (the fused multi-output kernel)."""
+    g.set_option("use_stream_kernel", 0)
+    try:
+        a, b = make_pair(41, 120_000, 90_000, 30_000, 25, "tail")
+        la, lb = g.WordList.from_arrays(*a, 25), g.WordList.from_arrays(*b, 25)
+        want = oracle.compare2(oracle.SList(*a, 25), oracle.SList(*b, 25), union=True, diff=True, cutoff=2)
+        for s, kw in (("union", dict(find_union=1)), ("diff1", dict(find_diff=1))):
+            w, c = g.compare_wordmaps(la, lb, cutoff=2, **kw)[s].to_host()
+            assert np.array_equal(w, want[s].words) and np.array_equal(c, want[s].counts)
+    finally:
+        g.set_option("use_stream_kernel", 1)
+
+
 def test_multi_golden_matrix(g, multi_lists):
     for gold in GOLDEN["multi"]:
         k, lists = multi_lists[gold["input"]]
