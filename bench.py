@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=float, default=1e8, help="k-mers per list of the CPU baseline sample")
     ap.add_argument("--ref-sample", type=float, default=4e7, help="k-mers per list per step of --impl reference")
     ap.add_argument("--tile", type=str, default=None, help="multi-output kernel tile, e.g. 256x9")
-    ap.add_argument("--stream-items", type=int, default=None, help="items per thread of the single-output kernel (7/9/11/13)")
+    ap.add_argument("--stream-shape", type=str, default=None, help="single-output kernel: consumers x items, e.g. 512x11")
     ap.add_argument("--no-stream-kernel", action="store_true", help="route the merge through setop2_tile_kernel")
     return ap.parse_args()
 
@@ -268,8 +268,11 @@ def run_gt4gpu_arm(args):
     if args.tile:
         nt, vt = args.tile.split("x")
         g.set_tile(int(nt), int(vt))
-    if args.stream_items:
-        g.set_option("stream_items", args.stream_items)
+    if args.stream_shape:
+        nc, vt = args.stream_shape.split("x")
+        g.set_option("stream_items", 7)
+        g.set_option("stream_consumers", int(nc))
+        g.set_option("stream_items", int(vt))
     if args.no_stream_kernel:
         g.set_option("use_stream_kernel", 0)
     g.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -365,7 +368,7 @@ def run_gt4gpu_arm(args):
                 "dtype": "u64 keys / u32 counts (integer compare, add mod 2^32)", "data": "synthetic",
                 "config": workload_config(args, na, nb), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks,
-                "output_kmers": total_out, "input_kmers": total_in, "kernel_config": {"kernel": kernel_name, "stream_items": args.stream_items or int(os.environ.get("GT4GPU_STREAM_ITEMS", "9")),
+                "output_kmers": total_out, "input_kmers": total_in, "kernel_config": {"kernel": kernel_name, "stream_shape": args.stream_shape or os.environ.get("GT4GPU_STREAM_SHAPE", "512x11"),
                                   "tile": args.tile or os.environ.get("GT4GPU_TILE", "256x9")}}
         print(json.dumps(line), flush=True)
     if world > 1:

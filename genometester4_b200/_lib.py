@@ -11,7 +11,8 @@ CSRC = PKG / "csrc"
 
 
 def lib_path() -> Path:
-    return PKG / "libgt4gpu.so"
+    import os
+    return Path(os.environ["GT4GPU_LIB"]) if os.environ.get("GT4GPU_LIB") else PKG / "libgt4gpu.so"
 
 
 def cli_path() -> Path:

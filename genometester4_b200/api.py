@@ -59,7 +59,7 @@ def set_tile(threads: int, items: int) -> None:
 
 
 def set_option(name: str, value: int) -> None:
-    """Tuning knobs of the library: "stream_items" (7/9/11/13), "use_stream_kernel" (0/1)."""
+    """Tuning knobs of the library: "stream_consumers" (256/512), "stream_items" (7/9/11), "use_stream_kernel" (0/1)."""
     _check(_lib.load().gt4gpu_set_option(name.encode(), int(value)))
 
 

@@ -46,7 +46,8 @@ struct Context {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   TileShape shape = {256, 9};   // tile shape of the multi-output kernel (setop2_tile_kernel)
-  int stream_items = 9;         // items per thread of the single-output kernel (setop2_stream_kernel)
+  int stream_consumers = 512;   // consumer threads per CTA of the single-output kernel (setop2_stream_kernel)
+  int stream_items = 11;        // its merged items per thread
   int use_stream = 1;           // 0: run single-output merges through setop2_tile_kernel too
   int sm_count = 0;
 };
@@ -126,7 +127,7 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   const int ns = (n_req == 1) ? 1 : 4;
   const TileShape shape = g_ctx.shape;
   const bool use_stream = (n_req == 1) && g_ctx.use_stream;
-  const uint64_t tile = use_stream ? (uint64_t) stream_tile_size (g_ctx.stream_items) : (uint64_t) shape.threads * shape.items;
+  const uint64_t tile = use_stream ? (uint64_t) g_ctx.stream_consumers * g_ctx.stream_items : (uint64_t) shape.threads * shape.items;
   const uint64_t n_tiles = (total + tile - 1) / tile;
   cudaStream_t st = g_ctx.stream;
 
@@ -165,6 +166,7 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   args.p = p;
   args.p.ops = stream_mask;
   args.stream0 = __builtin_ctz (stream_mask);
+  args.debug = getenv ("GT4GPU_DEBUG") ? atoi (getenv ("GT4GPU_DEBUG")) : 0;
   for (int s = 0; s < 4; s++) {
     args.out_words[s] = out[s].words;
     args.out_counts[s] = out[s].counts;
@@ -175,7 +177,7 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   CU (cudaEventRecord (tl_ev[0], st));
   CU (launch_partition (a.words, a.n, b.words, b.n, (uint32_t) tile, n_tiles, part, st));
   CU (cudaEventRecord (tl_ev[1], st));
-  if (use_stream) CU (launch_setop2_stream (args, g_ctx.stream_items, countonly, g_ctx.sm_count, st));
+  if (use_stream) CU (launch_setop2_stream (args, g_ctx.stream_consumers, g_ctx.stream_items, countonly, g_ctx.sm_count, st));
   else CU (launch_setop2 (args, shape, ns, countonly, st));
   CU (cudaEventRecord (tl_ev[2], st));
 
@@ -469,10 +471,13 @@ int gt4gpu_init (int device)
   uint64_t keep = UINT64_MAX;
   CU (cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep));
   CU (cudaDeviceGetAttribute (&g_ctx.sm_count, cudaDevAttrMultiProcessorCount, g_ctx.device));
-  const char *env = getenv ("GT4GPU_STREAM_ITEMS");   // items per thread of the single-output kernel
+  const char *env = getenv ("GT4GPU_STREAM_SHAPE");   // single-output kernel, e.g. GT4GPU_STREAM_SHAPE=512x11
   if (env) {
-    if (!stream_shape_supported (atoi (env))) return fail (GT4GPU_ERR_ARG, "GT4GPU_STREAM_ITEMS=%s is not supported", env);
-    g_ctx.stream_items = atoi (env);
+    int nc = 0, vt = 0;
+    if (sscanf (env, "%dx%d", &nc, &vt) != 2 || !stream_shape_supported (nc, vt))
+      return fail (GT4GPU_ERR_ARG, "GT4GPU_STREAM_SHAPE=%s is not supported", env);
+    g_ctx.stream_consumers = nc;
+    g_ctx.stream_items = vt;
   }
   env = getenv ("GT4GPU_USE_STREAM_KERNEL");
   if (env) g_ctx.use_stream = atoi (env) != 0;
@@ -516,8 +521,13 @@ int gt4gpu_set_option (const char *name, int value)
 {
   if (!name) return fail (GT4GPU_ERR_ARG, "null option name");
   if (!strcmp (name, "stream_items")) {
-    if (!stream_shape_supported (value)) return fail (GT4GPU_ERR_ARG, "stream_items=%d is not supported", value);
+    if (!stream_shape_supported (g_ctx.stream_consumers, value)) return fail (GT4GPU_ERR_ARG, "stream shape %dx%d is not supported", g_ctx.stream_consumers, value);
     g_ctx.stream_items = value;
+    return 0;
+  }
+  if (!strcmp (name, "stream_consumers")) {
+    if (!stream_shape_supported (value, g_ctx.stream_items)) return fail (GT4GPU_ERR_ARG, "stream shape %dx%d is not supported", value, g_ctx.stream_items);
+    g_ctx.stream_consumers = value;
     return 0;
   }
   if (!strcmp (name, "use_stream_kernel")) {

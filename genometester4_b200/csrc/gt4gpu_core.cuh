@@ -216,12 +216,13 @@ GT4_UNROLL
     const bool a_avail = i < na;
     const bool b_avail = j < nb;
     const bool take_a = a_avail && (!b_avail || key_a <= key_b);
-    const uint32_t cnt_a = ca[i];
-    const uint32_t cnt_b = cb[j];
     const bool pair = take_a && (j < nb_ext) && (key_b == key_a);
     const bool dup_b = !take_a && prev_ok && (prev_a == key_b);
     const bool live = (d0 + s < n_tile) && !dup_b;
-    sink (s, take_a ? key_a : key_b, cnt_a, cnt_b, take_a, !take_a || pair, live);
+    // one count load for the slot's own element, a second one only for the B half of a pair
+    const uint32_t cnt_self = *(take_a ? ca + i : cb + j);
+    const uint32_t cnt_pair = pair ? cb[j] : 0u;
+    sink (s, take_a ? key_a : key_b, cnt_self, take_a ? cnt_pair : cnt_self, take_a, !take_a || pair, live);
     if (take_a) {
       prev_a = key_a;
       prev_ok = true;

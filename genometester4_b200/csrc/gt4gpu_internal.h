@@ -39,6 +39,7 @@ struct TileArgs {
   CallHeader *hdr;
   uint64_t *desc;              // look-back descriptors, [stream slot][n_tiles]
   int stream0;                 // the single requested stream when the 1-stream kernel is used
+  int debug;                   // experiments only (GT4GPU_DEBUG): bit 0 = skip the look-back (WRONG output offsets)
   SetOpParams p;
 };
 
@@ -54,10 +55,9 @@ cudaError_t launch_partition (const uint64_t *a, uint64_t na, const uint64_t *b,
 cudaError_t launch_setop2 (const TileArgs &args, TileShape shape, int n_streams, bool count_only, cudaStream_t st);
 
 // second-generation single-output kernel (gt4gpu_stream_kernel.cu): persistent, warp-specialised, TMA-staged;
-// tiles are 256 * items merged slots
-bool stream_shape_supported (int items);
-int stream_tile_size (int items);
-cudaError_t launch_setop2_stream (const TileArgs &args, int items, bool count_only, int sm_count, cudaStream_t st);
+// tiles are consumers * items merged slots
+bool stream_shape_supported (int consumers, int items);
+cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items, bool count_only, int sm_count, cudaStream_t st);
 
 cudaError_t launch_deinterleave (const void *records, uint64_t n, uint64_t *words, uint32_t *counts, cudaStream_t st);
 cudaError_t launch_interleave (const uint64_t *words, const uint32_t *counts, uint64_t n, void *records, cudaStream_t st);

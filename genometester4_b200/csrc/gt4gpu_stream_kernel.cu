@@ -1,27 +1,29 @@
 // gt4gpu_stream_kernel.cu -- the single-output merge kernel, second generation.
 //
-// setop2_stream_kernel is a persistent, warp-specialised sm_100a kernel.  One CTA = 10 warps:
+// setop2_stream_kernel is a persistent, warp-specialised sm_100a kernel.  One CTA:
 //
-//   warps 0-7  consumers   per tile: wait for the stage, per-thread co-rank + serial merge of VT
-//                          slots out of shared memory (gt4gpu_core.cuh), predicate + count rule
-//                          (compile-time fast paths), block scan of the survivors, hand the tile
-//                          count to the look-back warp, store the PREVIOUS tile (whose global
-//                          offset has arrived meanwhile) with coalesced stores, then compact the
-//                          current tile's survivors into its own stage buffer
-//   warp 8     producer    claims tiles in order from a global ticket, reads their co-ranks and
-//                          stages the four slices (A keys, A counts, B keys, B counts, +1 halo /
-//                          +1 peek) with 1-D TMA bulk copies (cp.async.bulk, 16-byte aligned
-//                          over-fetch) that complete on the stage's "full" mbarrier
-//   warp 9     look-back   decoupled look-back over the per-tile descriptors; runs one tile
-//                          behind the consumers, so its L2 round trips are never on their
-//                          critical path
+//   warps 0..NC/32-1  consumers   per tile: wait for the stage, per-thread co-rank + serial merge
+//                          of VT slots out of shared memory (gt4gpu_core.cuh), predicate + count
+//                          rule (compile-time fast paths), block scan of the survivors, hand the
+//                          tile count to the look-back warp, compact the survivors to the front of
+//                          the stage buffer.  They never wait for a global offset.
+//   producer warp     claims tiles in order from a global ticket, reads their co-ranks and stages
+//                          the four slices (A keys, A counts, B keys, B counts, +1 halo / +1 peek)
+//                          with 1-D TMA bulk copies (cp.async.bulk, 16-byte aligned over-fetch)
+//                          that complete on the stage's "full" mbarrier
+//   S look-back warps decoupled look-back over the per-tile descriptors, one warp per stage so that
+//                          several tiles of the CTA resolve their offsets concurrently
+//   2 store warps     once a tile is compacted AND its global offset is known, copy its records
+//                          from the stage buffer to the output arrays (coalesced) and hand the
+//                          stage back to the producer
 //
-// Stages cycle  fill (TMA) -> merge -> hold the compacted output -> store -> free  through
-// mbarriers (full / empty / count posted / offset ready); with 3 stages the loads of tile n+2 are
-// in flight while tile n+1 is merged and tile n is stored.  The only CTA-wide synchronisation of
-// the consumers is one named barrier per tile (inside the scan).  Tiles are claimed through an
-// atomic ticket, so a tile's predecessors are always owned by CTAs that are already running and
-// the look-back cannot deadlock whatever the residency of the grid.
+// Stages cycle  fill (TMA) -> merge + compact -> await offset -> store -> free  through mbarriers
+// (full / compacted / count posted / offset ready / empty).  With S stages the consumers can run
+// S - 2 tiles ahead of the slowest look-back, so the L2 round trips of the prefix chain and the
+// skew between CTAs stay off their critical path.  The only CTA-wide synchronisation of the
+// consumers is one named barrier per tile (inside the scan).  Tiles are claimed through an atomic
+// ticket, so a tile's predecessors are always owned by CTAs that are already running and the
+// look-back cannot deadlock whatever the residency of the grid.
 //
 // HBM-bound integer work: no tensor cores.  Algorithmic traffic 12 B per input record + 12 B per
 // output record.
@@ -34,26 +36,30 @@ namespace gt4gpu {
 
 namespace {
 
-constexpr int CONSUMERS = 256;                 // 8 consumer warps
-constexpr int PRODUCER_WARP = CONSUMERS / 32;  // warp 8
-constexpr int LOOKBACK_WARP = PRODUCER_WARP + 1;
-constexpr int NTHREADS = CONSUMERS + 64;
-constexpr int STAGES = 3;
+constexpr int STORE_WARPS = 2;
 constexpr uint64_t TILE_END = ~0ull;
 
 constexpr uint64_t DESC_PARTIAL = 1ull << 62;
 constexpr uint64_t DESC_INCLUSIVE = 2ull << 62;
 constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1;
 
-template <int VT>
+// NC consumer threads (warps 0 .. NC/32-1), then the producer warp, the look-back warp and the store warps
+template <int NC, int VT, int S>
 struct StreamCfg {
+  static constexpr int CONSUMERS = NC;
+  static constexpr int STAGES = S;
+  static constexpr int PRODUCER_WARP = NC / 32;
+  static constexpr int LOOKBACK_WARP0 = NC / 32 + 1;          // one look-back warp per stage
+  static constexpr int STORE_WARP0 = LOOKBACK_WARP0 + S;
+  static constexpr int NTHREADS = NC + 32 + 32 * S + 32 * STORE_WARPS;
+  static constexpr int MIN_CTAS = (NC <= 256) ? 2 : 1;
   static constexpr int TILE = CONSUMERS * VT;
   // A and B slices are over-fetched to 16-byte boundaries on both sides and carry +1 halo / +1 peek;
   // merge_slots may read VT + 1 elements past a slice
   static constexpr int KSLOTS = (TILE + VT + 16 + 1) & ~1;
   static constexpr int CSLOTS = (TILE + VT + 28 + 3) & ~3;
   static constexpr size_t STAGE_BYTES = (size_t) KSLOTS * 8 + (size_t) CSLOTS * 4;
-  static constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES;
+  static constexpr size_t SMEM_BYTES = S * STAGE_BYTES;
 };
 
 struct StageMeta {
@@ -110,7 +116,8 @@ __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, uint32_t b
 
 __device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init () { asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void consumer_sync () { asm volatile ("bar.sync 1, %0;" :: "n"(CONSUMERS) : "memory"); }
+template <int NC>
+__device__ __forceinline__ void consumer_sync () { asm volatile ("bar.sync 1, %0;" :: "n"(NC) : "memory"); }
 
 __device__ __forceinline__ uint64_t ld_relaxed (const uint64_t *p)
 {
@@ -131,7 +138,19 @@ __device__ __forceinline__ uint64_t warp_sum_u64 (uint64_t v)
   return v;
 }
 
-// all 32 lanes of the look-back warp; returns the exclusive prefix of `aggregate`
+// All 32 lanes of the look-back warp; returns the exclusive prefix of `aggregate`.
+//
+// The chain of prefixes has to advance as fast as tiles are produced (~50-100 tiles/us at the HBM
+// roofline) and every hop costs an L2 round trip, so one hop inspects LB_W rows of 32 descriptors
+// (row k, lane l -> tile pred - 32 k - l: every row is one coalesced 256-byte request) instead of
+// the textbook single row.  Rows are consumed nearest-first; only a descriptor NEARER than the
+// nearest inclusive one can make the warp wait, and then only its row is polled again, with a
+// back-off, so that the few cache lines around the frontier are not hammered by every CTA.
+#ifndef GT4_LB_W
+#define GT4_LB_W 4
+#endif
+constexpr int LB_W = GT4_LB_W;
+
 __device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t tile, uint64_t aggregate, int lane)
 {
   if (tile == 0) {
@@ -139,44 +158,66 @@ __device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t
     return 0;
   }
   if (lane == 0) st_relaxed (desc + tile, DESC_PARTIAL | aggregate);
-  uint64_t exclusive = 0;
-  int64_t pred = (int64_t) tile - 1;
-  while (true) {
-    const int64_t idx = pred - lane;
-    uint64_t d = (idx >= 0) ? ld_relaxed (desc + idx) : DESC_INCLUSIVE;
-    while (__any_sync (0xffffffffu, (d >> 62) == 0)) {
-      if ((d >> 62) == 0) d = ld_relaxed (desc + idx);
+  uint64_t lane_sum = 0;
+  int64_t pred = (int64_t) tile - 1 - lane;
+  bool done = false;
+  while (!done) {
+    uint64_t d[LB_W];
+#pragma unroll
+    for (int k = 0; k < LB_W; k++) d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
+#pragma unroll
+    for (int k = 0; k < LB_W; k++) {
+      if (done) break;
+      while (true) {
+        const uint32_t st = (uint32_t) (d[k] >> 62);
+        const uint32_t m_wait = __ballot_sync (0xffffffffu, st == 0);
+        const uint32_t m_incl = __ballot_sync (0xffffffffu, st == 2);
+        const uint32_t m_stop = m_wait | m_incl;
+        if (m_stop == 0) {                     // a full row of partial counts
+          lane_sum += d[k] & DESC_VALUE_MASK;
+          break;
+        }
+        const int first = __ffs (m_stop) - 1;
+        if ((m_wait >> first) & 1u) {          // the nearest stopper has not posted yet: poll this row again
+          d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
+          continue;
+        }
+        if (lane <= first) lane_sum += d[k] & DESC_VALUE_MASK;
+        done = true;
+        break;
+      }
     }
-    const uint32_t incl = __ballot_sync (0xffffffffu, (d >> 62) == 2);
-    if (incl) {
-      const int first = __ffs (incl) - 1;
-      exclusive += warp_sum_u64 (lane <= first ? (d & DESC_VALUE_MASK) : 0ull);
-      break;
-    }
-    exclusive += warp_sum_u64 (d & DESC_VALUE_MASK);
-    pred -= 32;
+    pred -= 32 * LB_W;
   }
+  const uint64_t exclusive = warp_sum_u64 (lane_sum);
   if (lane == 0) st_relaxed (desc + tile, DESC_INCLUSIVE | (exclusive + aggregate));
   return exclusive;
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-template <int VT, int FAST, bool COUNT_ONLY>
-__global__ void __launch_bounds__ (NTHREADS, 2)
+template <int NC, int VT, int S, int FAST, bool COUNT_ONLY>
+__global__ void __launch_bounds__ (StreamCfg<NC, VT, S>::NTHREADS, StreamCfg<NC, VT, S>::MIN_CTAS)
 setop2_stream_kernel (const TileArgs args)
 {
-  using Cfg = StreamCfg<VT>;
+  using Cfg = StreamCfg<NC, VT, S>;
   constexpr int TILE = Cfg::TILE;
+  constexpr int STAGES = S;
+  constexpr int NWARPS = NC / 32;
+  constexpr int PRODUCER_WARP = Cfg::PRODUCER_WARP;
+  constexpr int LOOKBACK_WARP0 = Cfg::LOOKBACK_WARP0;
+  constexpr int STORE_WARP0 = Cfg::STORE_WARP0;
 
   extern __shared__ __align__ (128) unsigned char smem_raw[];
   __shared__ __align__ (8) uint64_t bar_full[STAGES];    // producer -> consumers: slices have landed (TMA tx)
-  __shared__ __align__ (8) uint64_t bar_empty[STAGES];   // consumers -> producer: stage may be refilled
+  __shared__ __align__ (8) uint64_t bar_comp[STAGES];    // consumers -> store warps: survivors compacted
   __shared__ __align__ (8) uint64_t bar_agg[STAGES];     // consumers -> look-back: tile count posted
-  __shared__ __align__ (8) uint64_t bar_base[STAGES];    // look-back -> consumers: global offset ready
+  __shared__ __align__ (8) uint64_t bar_base[STAGES];    // look-back -> store warps: global offset ready
+  __shared__ __align__ (8) uint64_t bar_empty[STAGES];   // store warps (count-only: consumers) -> producer
   __shared__ StageMeta s_meta[STAGES];
   __shared__ Mailbox s_mail[STAGES];
-  __shared__ int s_wcnt[2][CONSUMERS / 32];
-  __shared__ unsigned long long s_red[2][CONSUMERS / 32];
+  __shared__ int s_wcnt[2][NWARPS];
+  __shared__ volatile unsigned int s_n_iter;            // tiles this CTA ended up processing (set when the END marker arrives)
+  __shared__ unsigned long long s_red[2][NWARPS];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -186,10 +227,12 @@ setop2_stream_kernel (const TileArgs args)
 #pragma unroll
     for (int s = 0; s < STAGES; s++) {
       mbar_init (&bar_full[s], 1);
-      mbar_init (&bar_empty[s], CONSUMERS);
+      mbar_init (&bar_comp[s], NWARPS);
       mbar_init (&bar_agg[s], 1);
       mbar_init (&bar_base[s], 1);
+      mbar_init (&bar_empty[s], COUNT_ONLY ? NWARPS : STORE_WARPS);
     }
+    s_n_iter = 0xffffffffu;
     fence_mbar_init ();
   }
   __syncthreads ();
@@ -205,9 +248,9 @@ setop2_stream_kernel (const TileArgs args)
     uint64_t nxt = atomicAdd (&args.hdr->ticket, 1u);
     uint64_t nxt_lo = 0, nxt_hi = 0;
     if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
-    for (uint32_t it = 0;; it++) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1u;
+    int s = 0;
+    uint32_t ph = 0;
+    while (true) {
       const uint64_t tile = nxt, a_lo = nxt_lo, a_hi = nxt_hi;
       if (tile < n_tiles) {     // claim the following tile now: its latency hides behind the wait below
         nxt = atomicAdd (&args.hdr->ticket, 1u);
@@ -254,20 +297,23 @@ setop2_stream_kernel (const TileArgs args)
       if (bk_bytes) bulk_g2s (sk + (ak_bytes >> 3), (const void *) bk0a, bk_bytes, &bar_full[s]);
       if (ac_bytes) bulk_g2s (sc, (const void *) ac0a, ac_bytes, &bar_full[s]);
       if (bc_bytes) bulk_g2s (sc + (ac_bytes >> 2), (const void *) bc0a, bc_bytes, &bar_full[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     return;
   }
 
-  // ============================================================================ look-back
-  if (warp == LOOKBACK_WARP) {
+  // ============================================================================ look-back (one warp per stage)
+  // A look-back is a handful of dependent L2 round trips (microseconds under full memory load), longer
+  // than a tile period, so the tiles of one CTA are resolved by S warps in parallel: warp s owns stage s.
+  if (warp >= LOOKBACK_WARP0 && warp < STORE_WARP0) {
     if (COUNT_ONLY) return;
-    for (uint32_t it = 0;; it++) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1u;
+    const int s = warp - LOOKBACK_WARP0;
+    uint32_t ph = 0;
+    for (uint32_t it = (uint32_t) s;; it += STAGES, ph ^= 1u) {
       mbar_wait (&bar_agg[s], ph);
+      if (it >= s_n_iter) break;                  // the END marker, not a tile
       const uint64_t tile = s_mail[s].tile;
-      if (tile == TILE_END) break;
-      const uint64_t base = lookback_exclusive (args.desc, tile, (uint64_t) s_mail[s].cnt, lane);
+      const uint64_t base = (args.debug & 1) ? tile * TILE : lookback_exclusive (args.desc, tile, (uint64_t) s_mail[s].cnt, lane);
       if (lane == 0) {
         s_mail[s].base = base;
         mbar_arrive (&bar_base[s]);
@@ -277,45 +323,72 @@ setop2_stream_kernel (const TileArgs args)
     return;
   }
 
+  // ============================================================================ store warps
+  if (warp >= STORE_WARP0) {
+    if (COUNT_ONLY) return;
+    const int st_tid = tid - STORE_WARP0 * 32;
+    constexpr int ST_THREADS = 32 * STORE_WARPS;
+    const int stream = args.stream0;
+    int s = 0;
+    uint32_t ph = 0;
+    while (true) {
+      mbar_wait (&bar_comp[s], ph);
+      if (s_mail[s].tile == TILE_END) break;
+      mbar_wait (&bar_base[s], ph);
+      const uint64_t base = s_mail[s].base;
+      const int cnt = s_mail[s].cnt;
+      const uint64_t *sk = stage_keys (s);
+      const uint32_t *sc = stage_cnts (s);
+      if (base + (uint64_t) cnt <= args.out_capacity[stream]) {
+        uint64_t *ow = args.out_words[stream] + base;
+        uint32_t *oc = args.out_counts[stream] + base;
+        int x = st_tid;
+        for (; x + 7 * ST_THREADS < cnt; x += 8 * ST_THREADS) {
+          uint64_t k[8];
+#pragma unroll
+          for (int r = 0; r < 8; r++) k[r] = sk[x + r * ST_THREADS];
+#pragma unroll
+          for (int r = 0; r < 8; r++) ow[x + r * ST_THREADS] = k[r];
+        }
+        for (; x < cnt; x += ST_THREADS) ow[x] = sk[x];
+        x = st_tid;
+        for (; x + 7 * ST_THREADS < cnt; x += 8 * ST_THREADS) {
+          uint32_t c[8];
+#pragma unroll
+          for (int r = 0; r < 8; r++) c[r] = sc[x + r * ST_THREADS];
+#pragma unroll
+          for (int r = 0; r < 8; r++) oc[x + r * ST_THREADS] = c[r];
+        }
+        for (; x < cnt; x += ST_THREADS) oc[x] = sc[x];
+      } else if (st_tid == 0) {
+        args.hdr->overflow = 1u;
+      }
+      fence_proxy_async ();          // generic accesses to the stage before the async proxy (TMA) refills it
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (&bar_empty[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    return;
+  }
+
   // ============================================================================ consumers
   const int stream = args.stream0;
   unsigned long long acc_n = 0, acc_sum = 0;   // this thread's share of the header totals
-  int prev = -1, prev_cnt = 0;
-  uint32_t prev_ph = 0;
-
-  // store of a finished tile: its compacted records sit at the front of its stage buffer
-  auto store_tile = [&] (int s, int cnt, uint32_t ph) {
-    mbar_wait (&bar_base[s], ph);
-    const uint64_t base = s_mail[s].base;
-    const uint64_t *sk = stage_keys (s);
-    const uint32_t *sc = stage_cnts (s);
-    if (base + (uint64_t) cnt <= args.out_capacity[stream]) {
-      uint64_t *ow = args.out_words[stream] + base;
-      uint32_t *oc = args.out_counts[stream] + base;
-#pragma unroll
-      for (int r = 0; r < VT; r++) {
-        const int x = tid + r * CONSUMERS;
-        if (x < cnt) {
-          ow[x] = sk[x];
-          oc[x] = sc[x];
-        }
-      }
-    } else if (tid == 0) {
-      args.hdr->overflow = 1u;
-    }
-    fence_proxy_async ();          // generic accesses to the stage before the async proxy (TMA) refills it
-    mbar_arrive (&bar_empty[s]);
-  };
-
+  int s = 0;
+  uint32_t ph = 0;
   for (uint32_t it = 0;; it++) {
-    const int s = it % STAGES;
-    const uint32_t ph = (it / STAGES) & 1u;
     mbar_wait (&bar_full[s], ph);
     const StageMeta m = s_meta[s];
     if (m.tile == TILE_END) {
-      if (!COUNT_ONLY && tid == 0) {
-        s_mail[s].tile = TILE_END;
-        mbar_arrive (&bar_agg[s]);
+      if (!COUNT_ONLY) {
+        if (tid == 0) {
+          s_n_iter = it;                          // every look-back warp gets one last wake-up and sees it >= s_n_iter
+          s_mail[s].tile = TILE_END;              // safe: stage s was handed back by the store warps, so its mailbox is idle
+#pragma unroll
+          for (int q = 0; q < STAGES; q++) mbar_arrive (&bar_agg[q]);
+        }
+        __syncwarp ();
+        if (lane == 0) mbar_arrive (&bar_comp[s]);
       }
       break;
     }
@@ -346,7 +419,9 @@ setop2_stream_kernel (const TileArgs args)
     for (int sl = 0; sl < VT; sl++) acc_sum += ((mask >> sl) & 1u) ? o_freq[sl] : 0u;
 
     if (COUNT_ONLY) {
-      mbar_arrive (&bar_empty[s]);    // only generic reads touched the stage
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (&bar_empty[s]);    // only generic reads touched the stage
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
       continue;
     }
 
@@ -358,10 +433,10 @@ setop2_stream_kernel (const TileArgs args)
       if (lane >= off) incl += t;
     }
     if (lane == 31) s_wcnt[it & 1][warp] = incl;
-    consumer_sync ();               // also: every consumer is done reading this stage's inputs
+    consumer_sync<NC> ();           // also: every consumer is done reading this stage's inputs
     int warp_prefix = 0, tile_cnt = 0;
 #pragma unroll
-    for (int w = 0; w < CONSUMERS / 32; w++) {
+    for (int w = 0; w < NWARPS; w++) {
       const int v = s_wcnt[it & 1][w];
       if (w < warp) warp_prefix += v;
       tile_cnt += v;
@@ -372,10 +447,7 @@ setop2_stream_kernel (const TileArgs args)
       mbar_arrive (&bar_agg[s]);    // the look-back warp takes it from here
     }
 
-    // the previous tile's offset has had a whole merge phase to arrive
-    if (prev >= 0) store_tile (prev, prev_cnt, prev_ph);
-
-    // compact this tile's survivors to the front of its own stage buffer
+    // compact this tile's survivors to the front of its own stage buffer, then hand it to the store warps
     int pos = warp_prefix + incl - cnt;
 #pragma unroll
     for (int sl = 0; sl < VT; sl++) {
@@ -385,14 +457,9 @@ setop2_stream_kernel (const TileArgs args)
         pos += 1;
       }
     }
-    prev = s;
-    prev_cnt = tile_cnt;
-    prev_ph = ph;
-  }
-
-  if (!COUNT_ONLY) {
-    consumer_sync ();               // the last tile's compaction is complete
-    if (prev >= 0) store_tile (prev, prev_cnt, prev_ph);
+    __syncwarp ();
+    if (lane == 0) mbar_arrive (&bar_comp[s]);
+    if (++s == STAGES) { s = 0; ph ^= 1u; }
   }
 
   // header totals: one pair of atomics per CTA
@@ -402,11 +469,11 @@ setop2_stream_kernel (const TileArgs args)
     s_red[0][warp] = acc_n;
     s_red[1][warp] = acc_sum;
   }
-  consumer_sync ();
+  consumer_sync<NC> ();
   if (tid == 0) {
     unsigned long long n = 0, sum = 0;
 #pragma unroll
-    for (int w = 0; w < CONSUMERS / 32; w++) {
+    for (int w = 0; w < NWARPS; w++) {
       n += s_red[0][w];
       sum += s_red[1][w];
     }
@@ -417,12 +484,13 @@ setop2_stream_kernel (const TileArgs args)
 }
 
 // ---- launch ------------------------------------------------------------------------------------
-template <int VT, int FAST, bool CO>
+template <int NC, int VT, int S, int FAST, bool CO>
 cudaError_t launch_stream_one (const TileArgs &args, int sm_count, cudaStream_t st)
 {
-  using Cfg = StreamCfg<VT>;
+  using Cfg = StreamCfg<NC, VT, S>;
+  constexpr int NTHREADS = Cfg::NTHREADS;
   static int ctas_per_sm = 0;      // benign race: idempotent
-  auto kernel = setop2_stream_kernel<VT, FAST, CO>;
+  auto kernel = setop2_stream_kernel<NC, VT, S, FAST, CO>;
   if (ctas_per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -438,41 +506,40 @@ cudaError_t launch_stream_one (const TileArgs &args, int sm_count, cudaStream_t 
   return cudaGetLastError ();
 }
 
-template <int VT, bool CO>
+template <int NC, int VT, int S, bool CO>
 cudaError_t launch_stream_fast (const TileArgs &args, int fast, int sm_count, cudaStream_t st)
 {
   switch (fast) {
-  case FAST_U_ADD:  return launch_stream_one<VT, FAST_U_ADD, CO> (args, sm_count, st);
-  case FAST_I_MIN:  return launch_stream_one<VT, FAST_I_MIN, CO> (args, sm_count, st);
-  case FAST_D_SUB:  return launch_stream_one<VT, FAST_D_SUB, CO> (args, sm_count, st);
-  case FAST_NU_ADD: return launch_stream_one<VT, FAST_NU_ADD, CO> (args, sm_count, st);
-  case FAST_NI_MIN: return launch_stream_one<VT, FAST_NI_MIN, CO> (args, sm_count, st);
-  default:          return launch_stream_one<VT, FAST_GENERIC, CO> (args, sm_count, st);
+  case FAST_U_ADD:  return launch_stream_one<NC, VT, S, FAST_U_ADD, CO> (args, sm_count, st);
+  case FAST_I_MIN:  return launch_stream_one<NC, VT, S, FAST_I_MIN, CO> (args, sm_count, st);
+  case FAST_D_SUB:  return launch_stream_one<NC, VT, S, FAST_D_SUB, CO> (args, sm_count, st);
+  case FAST_NU_ADD: return launch_stream_one<NC, VT, S, FAST_NU_ADD, CO> (args, sm_count, st);
+  case FAST_NI_MIN: return launch_stream_one<NC, VT, S, FAST_NI_MIN, CO> (args, sm_count, st);
+  default:          return launch_stream_one<NC, VT, S, FAST_GENERIC, CO> (args, sm_count, st);
   }
 }
 
 }  // namespace
 
-#define GT4GPU_STREAM_VTS(X) X (7) X (9) X (11) X (13)
+// supported (consumer threads, items per thread, stages) triples; the stage count is fixed per shape by shared memory
+#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 4) X (256, 9, 3) X (256, 11, 3) X (512, 7, 4) X (512, 9, 4) X (512, 11, 3)
 
-bool stream_shape_supported (int items)
+bool stream_shape_supported (int consumers, int items)
 {
-#define X(VT) if (items == VT) return true;
-  GT4GPU_STREAM_VTS (X)
+#define X(NC, VT, S) if (consumers == NC && items == VT) return true;
+  GT4GPU_STREAM_SHAPES (X)
 #undef X
   return false;
 }
 
-int stream_tile_size (int items) { return CONSUMERS * items; }
-
-cudaError_t launch_setop2_stream (const TileArgs &args, int items, bool count_only, int sm_count, cudaStream_t st)
+cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items, bool count_only, int sm_count, cudaStream_t st)
 {
   if (args.n_tiles == 0) return cudaSuccess;
   const int fast = select_fast_path (args.p, args.stream0);
-#define X(VT)                                                                            \
-  if (items == VT) return count_only ? launch_stream_fast<VT, true> (args, fast, sm_count, st) \
-                                     : launch_stream_fast<VT, false> (args, fast, sm_count, st);
-  GT4GPU_STREAM_VTS (X)
+#define X(NC, VT, S)                                                                                        \
+  if (consumers == NC && items == VT) return count_only ? launch_stream_fast<NC, VT, S, true> (args, fast, sm_count, st) \
+                                                        : launch_stream_fast<NC, VT, S, false> (args, fast, sm_count, st);
+  GT4GPU_STREAM_SHAPES (X)
 #undef X
   return cudaErrorInvalidValue;
 }

@@ -13,7 +13,7 @@ from genometester4_b200 import synth
 
 n = float(sys.argv[1]) if len(sys.argv) > 1 else 1e9
 overlap = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
-shapes = [("stream", 7), ("stream", 9), ("stream", 11), ("stream", 13), (256, 7), (256, 9)]
+shapes = [("s256", 7), ("s256", 9), ("s256", 11), ("s512", 7), ("s512", 9), ("s512", 11), (256, 7)]
 g.init(0)
 g.set_stream(torch.cuda.current_stream().cuda_stream)
 m = int(round(2 * n - overlap * n))
@@ -28,8 +28,10 @@ rows = []
 for op, kw, name in (("union", dict(find_union=1), "union"), ("intersect", dict(find_intrsec=1), "intrsec"), ("diff", dict(find_diff=1), "diff1")):
     for countonly in (0, 1):
         for nt, vt in shapes:
-            if nt == "stream":
+            if isinstance(nt, str):
                 g.set_option("use_stream_kernel", 1)
+                g.set_option("stream_items", 7)
+                g.set_option("stream_consumers", int(nt[1:]))
                 g.set_option("stream_items", vt)
             else:
                 g.set_option("use_stream_kernel", 0)
