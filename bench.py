@@ -368,7 +368,7 @@ def run_gt4gpu_arm(args):
                 "dtype": "u64 keys / u32 counts (integer compare, add mod 2^32)", "data": "synthetic",
                 "config": workload_config(args, na, nb), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks,
-                "output_kmers": total_out, "input_kmers": total_in, "kernel_config": {"kernel": kernel_name, "stream_shape": args.stream_shape or os.environ.get("GT4GPU_STREAM_SHAPE", "512x11"),
+                "output_kmers": total_out, "input_kmers": total_in, "kernel_config": {"kernel": kernel_name, "stream_shape": args.stream_shape or os.environ.get("GT4GPU_STREAM_SHAPE", "512x9"),
                                   "tile": args.tile or os.environ.get("GT4GPU_TILE", "256x9")}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -47,7 +47,7 @@ struct Context {
   cudaStream_t stream = nullptr;
   TileShape shape = {256, 9};   // tile shape of the multi-output kernel (setop2_tile_kernel)
   int stream_consumers = 512;   // consumer threads per CTA of the single-output kernel (setop2_stream_kernel)
-  int stream_items = 11;        // its merged items per thread
+  int stream_items = 9;         // its merged items per thread
   int use_stream = 1;           // 0: run single-output merges through setop2_tile_kernel too
   int sm_count = 0;
 };
@@ -192,6 +192,15 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   tl_ms_merge += ms;
   tl_launches += 2;
 
+  if (args.debug & 2) {
+    unsigned long long v[4] = {0, 0, 0, 0};
+    for (int k = 0; k < TOTAL_SLOTS; k++) {
+      v[0] += h.totals[(args.stream0 + 1) & 3][k][0]; v[1] += h.totals[(args.stream0 + 1) & 3][k][1];
+      v[2] += h.totals[(args.stream0 + 2) & 3][k][0]; v[3] += h.totals[(args.stream0 + 2) & 3][k][1];
+    }
+    if (v[3]) fprintf (stderr, "gt4gpu debug: look-backs %llu, mean %.0f cycles, %.2f polls, %.2f extra hops\n", v[3],
+                       (double) v[0] / v[3], (double) v[1] / v[3], (double) v[2] / v[3] - 1.0);
+  }
   if (h.overflow) return fail (GT4GPU_ERR_CAPACITY, "output buffer too small for the merge result");
   for (int s = 0; s < 4; s++) {
     if (!((stream_mask >> s) & 1u)) continue;

@@ -190,47 +190,67 @@ GT4_HD Index merge_path (const uint64_t *a, Index na, const uint64_t *b, Index n
   return lo;
 }
 
+// Same search restricted to a window known from coarser diagonals: the co-rank is monotone in the
+// diagonal, so for D_lo <= diag <= D_hi it lies between the co-ranks of D_lo and D_hi.
+template <typename Index>
+GT4_HD Index merge_path_window (const uint64_t *a, Index na, const uint64_t *b, Index nb, Index diag, Index lo_hint, Index hi_hint)
+{
+  Index lo = diag > nb ? diag - nb : 0;
+  Index hi = diag < na ? diag : na;
+  if (lo < lo_hint) lo = lo_hint;
+  if (hi > hi_hint) hi = hi_hint;
+  while (lo < hi) {
+    const Index mid = lo + ((hi - lo) >> 1);
+    if (a[mid] <= b[diag - 1 - mid]) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
 // One thread's share of a tile: VT consecutive slots of the merged sequence starting at slot
 // `d0`, A-cursor `i0` (= merge_path (..., d0)).  ka/ca and kb/cb are the tile's slices; ka[-1] is
 // readable iff has_halo (the element of A just before the tile) and kb[nb] iff has_peek (the
 // element of B just after it).  Every distinct key is reported exactly once:
 //   - an A slot always reports, pairing with the next unconsumed B element when equal;
-//   - a B slot reports unless the A element just before it carries the same key (then the A
-//     slot -- possibly in the previous thread or tile -- already reported the pair).
-// sink (slot, key, c1, c2, in_a, in_b, live) is called for all VT slots; live == false marks
-// slots past the end of the tile or the second half of a pair.
+//   - the B slot that follows a paired A slot is the second half of that pair and is dead (it may
+//     be the first slot of the next thread or tile: then the element of A just before the cursor
+//     carries the same key).
+// sink (slot, key, c1, c2, in_a, in_b, live) is called for all VT slots; c1 is meaningful iff in_a,
+// c2 iff in_b; live == false marks slots past the end of the tile or the second half of a pair.
+// Cursors are kept as pointers so that the per-slot work is a handful of compares, two or three
+// shared-memory loads and predicated increments.
 template <int VT, typename Sink>
 GT4_HD void merge_slots (const uint64_t *ka, const uint32_t *ca, int na, bool has_halo,
                          const uint64_t *kb, const uint32_t *cb, int nb, bool has_peek,
                          int i0, int d0, Sink &&sink)
 {
-  const int n_tile = na + nb;
-  const int nb_ext = nb + (has_peek ? 1 : 0);
-  int i = i0, j = d0 - i0;
-  bool prev_ok = (i0 > 0) || has_halo;
-  uint64_t prev_a = prev_ok ? ka[i - 1] : 0ull;
-  uint64_t key_a = ka[i];     // may be past the slice: the buffers carry slack, value unused then
-  uint64_t key_b = kb[j];
+  const int n_live = na + nb - d0;                 // slots of this thread inside the tile (may exceed VT)
+  const uint64_t *pa = ka + i0, *pb = kb + (d0 - i0);
+  const uint32_t *pca = ca + i0, *pcb = cb + (d0 - i0);
+  const uint64_t *const a_end = ka + na, *const b_end = kb + nb, *const b_ext = b_end + (has_peek ? 1 : 0);
+  uint64_t key_a = *pa;       // may be past the slice: the buffers carry slack, value unused then
+  uint64_t key_b = *pb;
+  bool skip = ((i0 > 0) || has_halo) && (pb < b_ext) && (pa[-1] == key_b);
 GT4_UNROLL
   for (int s = 0; s < VT; s++) {
-    const bool a_avail = i < na;
-    const bool b_avail = j < nb;
+    const bool a_avail = pa < a_end;
+    const bool b_avail = pb < b_end;
     const bool take_a = a_avail && (!b_avail || key_a <= key_b);
-    const bool pair = take_a && (j < nb_ext) && (key_b == key_a);
-    const bool dup_b = !take_a && prev_ok && (prev_a == key_b);
-    const bool live = (d0 + s < n_tile) && !dup_b;
+    const bool pair = take_a && (pb < b_ext) && (key_b == key_a);
+    const bool live = (s < n_live) && !(skip && !take_a);
     // one count load for the slot's own element, a second one only for the B half of a pair
-    const uint32_t cnt_self = *(take_a ? ca + i : cb + j);
-    const uint32_t cnt_pair = pair ? cb[j] : 0u;
+    const uint32_t cnt_self = *(take_a ? pca : pcb);
+    const uint32_t cnt_pair = pair ? *pcb : 0u;
     sink (s, take_a ? key_a : key_b, cnt_self, take_a ? cnt_pair : cnt_self, take_a, !take_a || pair, live);
+    skip = pair;
     if (take_a) {
-      prev_a = key_a;
-      prev_ok = true;
-      i += 1;
-      key_a = ka[i];
+      pa += 1;
+      pca += 1;
+      key_a = *pa;
     } else {
-      j += 1;
-      key_b = kb[j];
+      pb += 1;
+      pcb += 1;
+      key_b = *pb;
     }
   }
 }

@@ -11,6 +11,8 @@
 //                          the four slices (A keys, A counts, B keys, B counts, +1 halo / +1 peek)
 //                          with 1-D TMA bulk copies (cp.async.bulk, 16-byte aligned over-fetch)
 //                          that complete on the stage's "full" mbarrier
+//   splitter warp     works ahead of the consumers on filled stages: full-depth co-rank searches for
+//                          every 8th consumer thread, so the consumers only search 8 * VT slots
 //   S look-back warps decoupled look-back over the per-tile descriptors, one warp per stage so that
 //                          several tiles of the CTA resolve their offsets concurrently
 //   2 store warps     once a tile is compacted AND its global offset is known, copy its records
@@ -36,7 +38,10 @@ namespace gt4gpu {
 
 namespace {
 
-constexpr int STORE_WARPS = 2;
+#ifndef GT4_STORE_WARPS
+#define GT4_STORE_WARPS 2
+#endif
+constexpr int STORE_WARPS = GT4_STORE_WARPS;
 constexpr uint64_t TILE_END = ~0ull;
 
 constexpr uint64_t DESC_PARTIAL = 1ull << 62;
@@ -49,9 +54,12 @@ struct StreamCfg {
   static constexpr int CONSUMERS = NC;
   static constexpr int STAGES = S;
   static constexpr int PRODUCER_WARP = NC / 32;
-  static constexpr int LOOKBACK_WARP0 = NC / 32 + 1;          // one look-back warp per stage
+  static constexpr int SPLITTER_WARP = NC / 32 + 1;
+  static constexpr int LOOKBACK_WARP0 = NC / 32 + 2;          // one look-back warp per stage
   static constexpr int STORE_WARP0 = LOOKBACK_WARP0 + S;
-  static constexpr int NTHREADS = NC + 32 + 32 * S + 32 * STORE_WARPS;
+  static constexpr int NTHREADS = NC + 64 + 32 * S + 32 * STORE_WARPS;
+  static constexpr int GROUP = NC / 32;                       // consumer threads per coarse co-rank: one splitter round of 32 searches
+  static constexpr int NSPLIT = NC / GROUP + 1;
   static constexpr int MIN_CTAS = (NC <= 256) ? 2 : 1;
   static constexpr int TILE = CONSUMERS * VT;
   // A and B slices are over-fetched to 16-byte boundaries on both sides and carry +1 halo / +1 peek;
@@ -107,11 +115,26 @@ __device__ __forceinline__ void mbar_wait (uint64_t *bar, uint32_t parity)
   while (!mbar_try_wait (bar, parity)) { }
 }
 
+// helper warps (producer, look-back, store) poll with a back-off so that their spinning does not take issue
+// slots from the consumer warps
+__device__ __forceinline__ void mbar_wait_relaxed (uint64_t *bar, uint32_t parity)
+{
+  while (!mbar_try_wait (bar, parity)) __nanosleep (128);
+}
+
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
   asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                 :: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
+}
+
+// L2 prefetch of a byte range (widened inwards to 16-byte boundaries; a few edge bytes do not matter)
+__device__ __forceinline__ void prefetch_l2 (const void *p, uint64_t bytes)
+{
+  const uintptr_t lo = ((uintptr_t) p + 15) & ~(uintptr_t) 15;
+  const uintptr_t hi = ((uintptr_t) p + bytes) & ~(uintptr_t) 15;
+  if (hi > lo) asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(lo), "r"((uint32_t) (hi - lo)) : "memory");
 }
 
 __device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -151,8 +174,12 @@ __device__ __forceinline__ uint64_t warp_sum_u64 (uint64_t v)
 #endif
 constexpr int LB_W = GT4_LB_W;
 
-__device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t tile, uint64_t aggregate, int lane)
+struct LookbackStats { unsigned long long cycles, polls, hops, calls; };
+
+__device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t tile, uint64_t aggregate, int lane, LookbackStats *stats = nullptr)
 {
+  const long long t_begin = stats ? clock64 () : 0;
+  unsigned polls = 0, hops = 0;
   if (tile == 0) {
     if (lane == 0) st_relaxed (desc, DESC_INCLUSIVE | aggregate);
     return 0;
@@ -179,6 +206,7 @@ __device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t
         }
         const int first = __ffs (m_stop) - 1;
         if ((m_wait >> first) & 1u) {          // the nearest stopper has not posted yet: poll this row again
+          polls++;
           d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
           continue;
         }
@@ -188,6 +216,13 @@ __device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t
       }
     }
     pred -= 32 * LB_W;
+    hops++;
+  }
+  if (stats) {
+    stats->cycles += (unsigned long long) (clock64 () - t_begin);
+    stats->polls += polls;
+    stats->hops += hops;
+    stats->calls += 1;
   }
   const uint64_t exclusive = warp_sum_u64 (lane_sum);
   if (lane == 0) st_relaxed (desc + tile, DESC_INCLUSIVE | (exclusive + aggregate));
@@ -204,17 +239,22 @@ setop2_stream_kernel (const TileArgs args)
   constexpr int STAGES = S;
   constexpr int NWARPS = NC / 32;
   constexpr int PRODUCER_WARP = Cfg::PRODUCER_WARP;
+  constexpr int SPLITTER_WARP = Cfg::SPLITTER_WARP;
   constexpr int LOOKBACK_WARP0 = Cfg::LOOKBACK_WARP0;
+  constexpr int GROUP = Cfg::GROUP;
+  constexpr int NSPLIT = Cfg::NSPLIT;
   constexpr int STORE_WARP0 = Cfg::STORE_WARP0;
 
   extern __shared__ __align__ (128) unsigned char smem_raw[];
   __shared__ __align__ (8) uint64_t bar_full[STAGES];    // producer -> consumers: slices have landed (TMA tx)
+  __shared__ __align__ (8) uint64_t bar_split[STAGES];   // splitter -> consumers: coarse co-ranks ready (implies full)
   __shared__ __align__ (8) uint64_t bar_comp[STAGES];    // consumers -> store warps: survivors compacted
   __shared__ __align__ (8) uint64_t bar_agg[STAGES];     // consumers -> look-back: tile count posted
   __shared__ __align__ (8) uint64_t bar_base[STAGES];    // look-back -> store warps: global offset ready
   __shared__ __align__ (8) uint64_t bar_empty[STAGES];   // store warps (count-only: consumers) -> producer
   __shared__ StageMeta s_meta[STAGES];
   __shared__ Mailbox s_mail[STAGES];
+  __shared__ int s_split[STAGES][NSPLIT];
   __shared__ int s_wcnt[2][NWARPS];
   __shared__ volatile unsigned int s_n_iter;            // tiles this CTA ended up processing (set when the END marker arrives)
   __shared__ unsigned long long s_red[2][NWARPS];
@@ -227,6 +267,7 @@ setop2_stream_kernel (const TileArgs args)
 #pragma unroll
     for (int s = 0; s < STAGES; s++) {
       mbar_init (&bar_full[s], 1);
+      mbar_init (&bar_split[s], 1);
       mbar_init (&bar_comp[s], NWARPS);
       mbar_init (&bar_agg[s], 1);
       mbar_init (&bar_base[s], 1);
@@ -248,18 +289,41 @@ setop2_stream_kernel (const TileArgs args)
     uint64_t nxt = atomicAdd (&args.hdr->ticket, 1u);
     uint64_t nxt_lo = 0, nxt_hi = 0;
     if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
+    // L2 prefetch of the tiles the grid will claim about two rounds from now (co-ranks loaded one iteration early)
+    const uint64_t pf_dist = (uint64_t) ((args.debug >> 4) ? (args.debug >> 4) : 1) * gridDim.x;
+    uint64_t pf_tile = nxt + pf_dist, pf_lo = 0, pf_hi = 0;
+    if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
     int s = 0;
     uint32_t ph = 0;
     while (true) {
       const uint64_t tile = nxt, a_lo = nxt_lo, a_hi = nxt_hi;
+      const uint64_t cur_pf = pf_tile, cur_pf_lo = pf_lo, cur_pf_hi = pf_hi;
       if (tile < n_tiles) {     // claim the following tile now: its latency hides behind the wait below
         nxt = atomicAdd (&args.hdr->ticket, 1u);
         if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
+        pf_tile = nxt + pf_dist;
+        if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
       }
-      mbar_wait (&bar_empty[s], ph ^ 1u);
+      if (!COUNT_ONLY && (args.debug & 4) == 0 && cur_pf < n_tiles) {   // (the count-only pass is faster without it)
+        const uint64_t pd_lo = cur_pf * TILE;
+        const uint64_t pd_hi = (pd_lo + TILE < total) ? pd_lo + TILE : total;
+        const uint64_t pb_lo = pd_lo - cur_pf_lo, pb_hi = pd_hi - cur_pf_hi;
+        prefetch_l2 (args.a_words + cur_pf_lo, (cur_pf_hi - cur_pf_lo) * 8);
+        prefetch_l2 (args.b_words + pb_lo, (pb_hi - pb_lo) * 8);
+        prefetch_l2 (args.a_counts + cur_pf_lo, (cur_pf_hi - cur_pf_lo) * 4);
+        prefetch_l2 (args.b_counts + pb_lo, (pb_hi - pb_lo) * 4);
+      }
+      mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
       if (tile >= n_tiles) {
-        s_meta[s].tile = TILE_END;
-        mbar_arrive (&bar_full[s]);
+        // out of work: send an END marker through EVERY stage, in order and under the normal stage protocol
+        // (each look-back warp owns one stage and must see its own marker; a barrier may never be advanced
+        // twice before its waiter has looked)
+        for (int q = 0; q < (COUNT_ONLY ? 1 : STAGES); q++) {
+          if (q > 0) mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
+          s_meta[s].tile = TILE_END;
+          mbar_arrive (&bar_full[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
         break;
       }
       const uint64_t d_lo = tile * TILE;
@@ -302,6 +366,38 @@ setop2_stream_kernel (const TileArgs args)
     return;
   }
 
+  // ============================================================================ splitter
+  // Works one or two tiles ahead of the consumers on the stages the TMA has already filled: co-rank of every
+  // GROUP-th consumer thread's diagonal over the whole tile (full-depth searches, 32 at a time), so that the
+  // consumers' own searches only span GROUP * VT slots.
+  if (warp == SPLITTER_WARP) {
+    int s = 0, n_end = 0;
+    uint32_t ph = 0;
+    while (true) {
+      mbar_wait (&bar_full[s], ph);
+      const StageMeta m = s_meta[s];
+      if (m.tile != TILE_END) {
+        const uint64_t *sk = stage_keys (s);
+        const uint64_t *ka = sk + m.ka, *kb = sk + m.kb;
+        const int n_tile = m.na + m.nb;
+#pragma unroll
+        for (int r = 0; r < (NSPLIT - 1 + 31) / 32; r++) {
+          const int g = lane + 32 * r;
+          if (g < NSPLIT - 1) {
+            const int dg = g * GROUP * VT;
+            s_split[s][g] = (dg < n_tile) ? merge_path<int> (ka, m.na, kb, m.nb, dg) : m.na;
+          }
+        }
+        if (lane == 0) s_split[s][NSPLIT - 1] = m.na;     // the diagonal at the end of the tile
+      }
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (&bar_split[s]);
+      if (m.tile == TILE_END && ++n_end == (COUNT_ONLY ? 1 : STAGES)) break;
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    return;
+  }
+
   // ============================================================================ look-back (one warp per stage)
   // A look-back is a handful of dependent L2 round trips (microseconds under full memory load), longer
   // than a tile period, so the tiles of one CTA are resolved by S warps in parallel: warp s owns stage s.
@@ -309,16 +405,26 @@ setop2_stream_kernel (const TileArgs args)
     if (COUNT_ONLY) return;
     const int s = warp - LOOKBACK_WARP0;
     uint32_t ph = 0;
+    LookbackStats stats = {0, 0, 0, 0};
     for (uint32_t it = (uint32_t) s;; it += STAGES, ph ^= 1u) {
-      mbar_wait (&bar_agg[s], ph);
+      mbar_wait_relaxed (&bar_agg[s], ph);
       if (it >= s_n_iter) break;                  // the END marker, not a tile
       const uint64_t tile = s_mail[s].tile;
-      const uint64_t base = (args.debug & 1) ? tile * TILE : lookback_exclusive (args.desc, tile, (uint64_t) s_mail[s].cnt, lane);
+      const uint64_t base = (args.debug & 1) ? tile * TILE
+                          : lookback_exclusive (args.desc, tile, (uint64_t) s_mail[s].cnt, lane, (args.debug & 2) ? &stats : nullptr);
       if (lane == 0) {
         s_mail[s].base = base;
         mbar_arrive (&bar_base[s]);
       }
       __syncwarp ();
+    }
+    if ((args.debug & 2) && lane == 0) {          // experiments: look-back latency statistics in the unused totals rows
+      unsigned long long *row = args.hdr->totals[(args.stream0 + 1) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
+      atomicAdd (row, stats.cycles);
+      atomicAdd (row + 1, stats.polls);
+      row = args.hdr->totals[(args.stream0 + 2) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
+      atomicAdd (row, stats.hops);
+      atomicAdd (row + 1, stats.calls);
     }
     return;
   }
@@ -332,9 +438,9 @@ setop2_stream_kernel (const TileArgs args)
     int s = 0;
     uint32_t ph = 0;
     while (true) {
-      mbar_wait (&bar_comp[s], ph);
-      if (s_mail[s].tile == TILE_END) break;
-      mbar_wait (&bar_base[s], ph);
+      mbar_wait_relaxed (&bar_comp[s], ph);
+      if (s_mail[s].tile == TILE_END) break;      // every real tile precedes the first END marker
+      mbar_wait_relaxed (&bar_base[s], ph);
       const uint64_t base = s_mail[s].base;
       const int cnt = s_mail[s].cnt;
       const uint64_t *sk = stage_keys (s);
@@ -374,23 +480,26 @@ setop2_stream_kernel (const TileArgs args)
   // ============================================================================ consumers
   const int stream = args.stream0;
   unsigned long long acc_n = 0, acc_sum = 0;   // this thread's share of the header totals
-  int s = 0;
+  int s = 0, n_end = 0;
   uint32_t ph = 0;
   for (uint32_t it = 0;; it++) {
-    mbar_wait (&bar_full[s], ph);
+    mbar_wait (&bar_split[s], ph);
+    mbar_wait (&bar_full[s], ph);        // already complete; observed directly for the TMA-written data
     const StageMeta m = s_meta[s];
     if (m.tile == TILE_END) {
-      if (!COUNT_ONLY) {
-        if (tid == 0) {
-          s_n_iter = it;                          // every look-back warp gets one last wake-up and sees it >= s_n_iter
-          s_mail[s].tile = TILE_END;              // safe: stage s was handed back by the store warps, so its mailbox is idle
-#pragma unroll
-          for (int q = 0; q < STAGES; q++) mbar_arrive (&bar_agg[q]);
-        }
-        __syncwarp ();
-        if (lane == 0) mbar_arrive (&bar_comp[s]);
+      if (COUNT_ONLY) break;
+      // END markers arrive on S consecutive stages; pass each one on to that stage's look-back warp
+      // (and the first one to the store warps)
+      if (tid == 0) {
+        if (it < s_n_iter) s_n_iter = it;
+        s_mail[s].tile = TILE_END;
+        mbar_arrive (&bar_agg[s]);
       }
-      break;
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (&bar_comp[s]);
+      if (++n_end == STAGES) break;
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+      continue;
     }
     uint64_t *sk = stage_keys (s);
     uint32_t *sc = stage_cnts (s);
@@ -400,7 +509,7 @@ setop2_stream_kernel (const TileArgs args)
     const uint32_t *cb = sc + m.cb;
     const int n_tile = m.na + m.nb;
     const int d0 = (tid * VT < n_tile) ? tid * VT : n_tile;
-    const int i0 = merge_path<int> (ka, m.na, kb, m.nb, d0);
+    const int i0 = merge_path_window<int> (ka, m.na, kb, m.nb, d0, s_split[s][tid / GROUP], s_split[s][tid / GROUP + 1]);
 
     uint64_t o_key[VT];
     uint32_t o_freq[VT];
@@ -522,7 +631,7 @@ cudaError_t launch_stream_fast (const TileArgs &args, int fast, int sm_count, cu
 }  // namespace
 
 // supported (consumer threads, items per thread, stages) triples; the stage count is fixed per shape by shared memory
-#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 4) X (256, 9, 3) X (256, 11, 3) X (512, 7, 4) X (512, 9, 4) X (512, 11, 3)
+#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 3) X (256, 11, 3) X (512, 7, 5) X (512, 8, 4) X (512, 9, 4) X (512, 10, 3) X (512, 11, 3) X (256, 8, 4) X (256, 10, 3)
 
 bool stream_shape_supported (int consumers, int items)
 {

@@ -46,9 +46,17 @@ static void run (const uint64_t *aw, const uint32_t *ac, uint64_t na, const uint
     const uint64_t *ka = sk.data () + 1; const uint32_t *ca = sc.data () + 1;
     const uint64_t *kb = ka + tna; const uint32_t *cb = ca + tna;
     const int n_tile = tna + tnb;
+    // coarse co-ranks every 8 threads (what the splitter warp of setop2_stream_kernel computes)
+    const int n_split = (nt + 7) / 8 + 1;
+    std::vector<int> split (n_split);
+    for (int g = 0; g < n_split; g++) {
+      const int dg = (g * 8 * VT < n_tile) ? g * 8 * VT : n_tile;
+      split[g] = merge_path<int> (ka, tna, kb, tnb, dg);
+    }
     for (int tid = 0; tid < nt; tid++) {
       const int d0 = (tid * VT < n_tile) ? tid * VT : n_tile;
-      const int i0 = merge_path<int> (ka, tna, kb, tnb, d0);
+      const int i0 = merge_path_window<int> (ka, tna, kb, tnb, d0, split[tid / 8], split[tid / 8 + 1]);
+      if (i0 != merge_path<int> (ka, tna, kb, tnb, d0)) __builtin_trap ();
       merge_slots<VT> (ka, ca, tna, has_halo, kb, cb, tnb, has_peek, i0, d0,
         [&] (int, uint64_t key, uint32_t c1, uint32_t c2, bool in_a, bool in_b, bool live) {
           for (int q = 0; q < 4; q++) {

@@ -145,7 +145,7 @@ def test_stream_kernel_every_shape_rule_and_semantics(g, oracle, shape):
     finally:
         g.set_option("stream_items", 7)
         g.set_option("stream_consumers", 512)
-        g.set_option("stream_items", 11)
+        g.set_option("stream_items", 9)
 
 
 def test_stream_kernel_misaligned_device_views(g, oracle):
