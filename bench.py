@@ -97,7 +97,7 @@ class ClockSampler:
         try:
             self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(self.index)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
