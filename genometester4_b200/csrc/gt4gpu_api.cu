@@ -45,6 +45,8 @@ struct Context {
   int device = -1;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t in_stream = nullptr;    // host-to-device copies of the pipelined host path
+  cudaStream_t out_stream = nullptr;   // device-to-host copies of the pipelined host path
   TileShape shape = {256, 9};   // tile shape of the multi-output kernel (setop2_tile_kernel)
   int stream_consumers = 512;   // consumer threads per CTA of the single-output kernel (setop2_stream_kernel)
   int stream_items = 9;         // its merged items per thread
@@ -474,6 +476,8 @@ int gt4gpu_init (int device)
   CU (cudaGetDevice (&g_ctx.device));
   if (!g_ctx.own_stream) CU (cudaStreamCreateWithFlags (&g_ctx.own_stream, cudaStreamNonBlocking));
   if (!g_ctx.stream) g_ctx.stream = g_ctx.own_stream;
+  if (!g_ctx.in_stream) CU (cudaStreamCreateWithFlags (&g_ctx.in_stream, cudaStreamNonBlocking));
+  if (!g_ctx.out_stream) CU (cudaStreamCreateWithFlags (&g_ctx.out_stream, cudaStreamNonBlocking));
   // keep freed blocks cached in the stream-ordered pool: per-call scratch and results then cost no driver call
   cudaMemPool_t pool;
   CU (cudaDeviceGetDefaultMemPool (&pool, g_ctx.device));
@@ -505,6 +509,8 @@ void gt4gpu_shutdown (void)
   if (!g_ctx.ready) return;
   cudaStreamSynchronize (g_ctx.stream);
   if (g_ctx.own_stream) cudaStreamDestroy (g_ctx.own_stream);
+  if (g_ctx.in_stream) cudaStreamDestroy (g_ctx.in_stream);
+  if (g_ctx.out_stream) cudaStreamDestroy (g_ctx.out_stream);
   g_ctx = Context ();
 }
 
@@ -943,13 +949,13 @@ void gt4gpu_result_free (gt4gpu_result *res)
 
 // ------------------------------------------------------------------ host-to-host
 
-int gt4gpu_compare2_host_aos (const void *records_a, uint64_t n_a, const void *records_b, uint64_t n_b,
-                              uint32_t word_length, uint32_t ops, int rule, uint32_t cutoff,
-                              uint32_t count_override, int subtract, int countonly,
-                              void *const out_records[4], const uint64_t out_capacity[4],
-                              uint64_t n_out[4], uint64_t total_out[4])
+// Small inputs: upload everything, merge once, download.
+static int compare2_host_simple (const void *records_a, uint64_t n_a, const void *records_b, uint64_t n_b,
+                                 uint32_t word_length, uint32_t ops, int rule, uint32_t cutoff,
+                                 uint32_t count_override, int subtract, int countonly,
+                                 void *const out_records[4], const uint64_t out_capacity[4],
+                                 uint64_t n_out[4], uint64_t total_out[4])
 {
-  if (!n_out || !total_out) return fail (GT4GPU_ERR_ARG, "null argument");
   gt4gpu_list *a = nullptr, *b = nullptr;
   int rc = gt4gpu_list_from_host_aos (records_a, n_a, word_length, &a);
   if (!rc) rc = gt4gpu_list_from_host_aos (records_b, n_b, word_length, &b);
@@ -972,6 +978,155 @@ int gt4gpu_compare2_host_aos (const void *records_a, uint64_t n_a, const void *r
   gt4gpu_list_close (b);
   tl_ms_partition = ms_p; tl_ms_merge = ms_m; tl_launches = nl;
   return rc;
+}
+
+// Large inputs: the key space is cut into parts (the same exact splitters the multi-GPU path uses, so equal keys
+// share a part and the concatenation of the per-part results IS the result); part p+1 is copied in and
+// de-interleaved on its own stream while part p is merged and part p-1 is interleaved and copied out on a third
+// stream.  PCIe is full duplex, so the whole call costs about max (H2D, D2H) instead of their sum.
+static int compare2_host_pipelined (const unsigned char *rec_a, uint64_t n_a, const unsigned char *rec_b, uint64_t n_b,
+                                    uint32_t word_length, uint32_t ops, int rule, uint32_t cutoff,
+                                    uint32_t count_override, int subtract, int countonly,
+                                    void *const out_records[4], const uint64_t out_capacity[4],
+                                    uint64_t n_out[4], uint64_t total_out[4], unsigned n_parts)
+{
+  (void) word_length;
+  std::vector<uint64_t> bounds (2 * (n_parts + 1));
+  {
+    const void *keys[2] = {rec_a, rec_b};
+    const size_t strides[2] = {12, 12};
+    const uint64_t sizes[2] = {n_a, n_b};
+    int rc = gt4gpu_plan_splitters (keys, strides, sizes, 2, n_parts, bounds.data (), nullptr);
+    if (rc) return rc;
+  }
+  const uint64_t *ba = bounds.data (), *bb = bounds.data () + n_parts + 1;
+  uint64_t max_a = 0, max_b = 0;
+  for (unsigned p = 0; p < n_parts; p++) {
+    max_a = std::max (max_a, ba[p + 1] - ba[p]);
+    max_b = std::max (max_b, bb[p + 1] - bb[p]);
+  }
+  SetOpParams prm;
+  memset (&prm, 0, sizeof (prm));
+  prm.ops = ops; prm.cutoff = cutoff; prm.count_override = count_override; prm.subtract = subtract ? 1 : 0; prm.sem = SEM_PAIR;
+  for (int s = 0; s < 4; s++) prm.rule[s] = resolve_rule (rule, s);
+
+  // two sets of device buffers
+  struct Set {
+    void *aos_a = nullptr, *aos_b = nullptr;
+    uint64_t *wa = nullptr, *wb = nullptr;
+    uint32_t *ca = nullptr, *cb = nullptr;
+    uint64_t *ow[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *oc[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *oaos[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t in_done = nullptr, merged = nullptr, out_done = nullptr;
+  } set[2];
+  uint64_t cap[4];
+  for (int s = 0; s < 4; s++) cap[s] = worst_case (prm, s, max_a, max_b);
+  int rc = 0;
+  auto alloc = [&] (void **p, size_t bytes) { if (!rc) rc = dev_alloc (p, bytes); };
+  for (int b = 0; b < 2; b++) {
+    alloc (&set[b].aos_a, max_a * 12); alloc (&set[b].aos_b, max_b * 12);
+    alloc ((void **) &set[b].wa, max_a * 8); alloc ((void **) &set[b].ca, max_a * 4);
+    alloc ((void **) &set[b].wb, max_b * 8); alloc ((void **) &set[b].cb, max_b * 4);
+    for (int s = 0; s < 4; s++) {
+      if (!((ops >> s) & 1u) || countonly) continue;
+      alloc ((void **) &set[b].ow[s], cap[s] * 8); alloc ((void **) &set[b].oc[s], cap[s] * 4); alloc (&set[b].oaos[s], cap[s] * 12);
+    }
+    if (!rc && (cudaEventCreateWithFlags (&set[b].in_done, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags (&set[b].merged, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags (&set[b].out_done, cudaEventDisableTiming) != cudaSuccess))
+      rc = fail (GT4GPU_ERR_CUDA, "cudaEventCreate failed");
+  }
+  cudaError_t e = cudaSuccess;
+  if (!rc) e = cudaStreamSynchronize (g_ctx.stream);     // the allocations above are ordered on the compute stream
+
+  auto enqueue_in = [&] (unsigned p) {
+    Set &st = set[p & 1];
+    const uint64_t na = ba[p + 1] - ba[p], nb = bb[p + 1] - bb[p];
+    // the merge that last read this set (part p - 2) has completed: merge2_device synchronises
+    if (na) {
+      e = cudaMemcpyAsync (st.aos_a, rec_a + ba[p] * 12, na * 12, cudaMemcpyHostToDevice, g_ctx.in_stream);
+      if (e == cudaSuccess) e = launch_deinterleave (st.aos_a, na, st.wa, st.ca, g_ctx.in_stream);
+    }
+    if (e == cudaSuccess && nb) {
+      e = cudaMemcpyAsync (st.aos_b, rec_b + bb[p] * 12, nb * 12, cudaMemcpyHostToDevice, g_ctx.in_stream);
+      if (e == cudaSuccess) e = launch_deinterleave (st.aos_b, nb, st.wb, st.cb, g_ctx.in_stream);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord (st.in_done, g_ctx.in_stream);
+  };
+
+  float ms_p = 0.f, ms_m = 0.f;
+  uint32_t nl = 0;
+  for (int s = 0; s < 4; s++) n_out[s] = total_out[s] = 0;
+  if (!rc && e == cudaSuccess) enqueue_in (0);
+  for (unsigned p = 0; p < n_parts && !rc && e == cudaSuccess; p++) {
+    Set &st = set[p & 1];
+    if (p + 1 < n_parts) enqueue_in (p + 1);
+    if (e != cudaSuccess) break;
+    e = cudaStreamWaitEvent (g_ctx.stream, st.in_done, 0);
+    if (e == cudaSuccess && p >= 2) e = cudaStreamWaitEvent (g_ctx.stream, st.out_done, 0);   // its output buffers were copied out
+    if (e != cudaSuccess) break;
+    MergeOut mo[4];
+    for (int s = 0; s < 4; s++) {
+      if (!((ops >> s) & 1u) || countonly) continue;
+      mo[s].caller = true; mo[s].words = st.ow[s]; mo[s].counts = st.oc[s]; mo[s].capacity = cap[s];
+    }
+    reset_timing ();
+    rc = merge2_device (DevList{st.wa, st.ca, ba[p + 1] - ba[p]}, DevList{st.wb, st.cb, bb[p + 1] - bb[p]}, prm, ops, countonly != 0, mo);
+    ms_p += tl_ms_partition; ms_m += tl_ms_merge; nl += tl_launches;
+    if (rc) break;
+    for (int s = 0; s < 4; s++) {
+      if (!((ops >> s) & 1u)) continue;
+      if (!countonly && mo[s].n) {
+        if (!out_records || !out_capacity || !out_records[s]) { rc = fail (GT4GPU_ERR_ARG, "missing output buffer for stream %d", s); break; }
+        if (n_out[s] + mo[s].n > out_capacity[s]) { rc = fail (GT4GPU_ERR_CAPACITY, "stream %d needs more than %llu records", s, (unsigned long long) out_capacity[s]); break; }
+        e = launch_interleave (st.ow[s], st.oc[s], mo[s].n, st.oaos[s], g_ctx.out_stream);     // merge p is complete (synchronised)
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync (static_cast<unsigned char *> (out_records[s]) + n_out[s] * 12, st.oaos[s], mo[s].n * 12, cudaMemcpyDeviceToHost, g_ctx.out_stream);
+        if (e != cudaSuccess) break;
+      }
+      n_out[s] += mo[s].n;
+      total_out[s] += mo[s].sum;
+    }
+    if (e == cudaSuccess) e = cudaEventRecord (st.out_done, g_ctx.out_stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.out_stream);
+  cudaStreamSynchronize (g_ctx.in_stream);
+  for (int b = 0; b < 2; b++) {
+    dev_free (set[b].aos_a); dev_free (set[b].aos_b); dev_free (set[b].wa); dev_free (set[b].ca); dev_free (set[b].wb); dev_free (set[b].cb);
+    for (int s = 0; s < 4; s++) { dev_free (set[b].ow[s]); dev_free (set[b].oc[s]); dev_free (set[b].oaos[s]); }
+    if (set[b].in_done) cudaEventDestroy (set[b].in_done);
+    if (set[b].merged) cudaEventDestroy (set[b].merged);
+    if (set[b].out_done) cudaEventDestroy (set[b].out_done);
+  }
+  tl_ms_partition = ms_p; tl_ms_merge = ms_m; tl_launches = nl;
+  if (!rc && e != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "pipelined host path: %s", cudaGetErrorString (e));
+  return rc;
+}
+
+int gt4gpu_compare2_host_aos (const void *records_a, uint64_t n_a, const void *records_b, uint64_t n_b,
+                              uint32_t word_length, uint32_t ops, int rule, uint32_t cutoff,
+                              uint32_t count_override, int subtract, int countonly,
+                              void *const out_records[4], const uint64_t out_capacity[4],
+                              uint64_t n_out[4], uint64_t total_out[4])
+{
+  if (!n_out || !total_out) return fail (GT4GPU_ERR_ARG, "null argument");
+  if (!ops || (ops & ~15u)) return fail (GT4GPU_ERR_ARG, "ops must be a non-empty OR of GT4GPU_OP_*");
+  if (rule < GT4GPU_RULE_DEFAULT || rule > GT4GPU_RULE_NUMBER) return fail (GT4GPU_ERR_ARG, "unknown rule %d", rule);
+  if ((n_a && !records_a) || (n_b && !records_b)) return fail (GT4GPU_ERR_ARG, "null argument");
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  const uint64_t total = n_a + n_b;
+  uint64_t part_records = 64ull << 20;             // records per part (768 MiB of input)
+  if (const char *env = getenv ("GT4GPU_HOST_PART_RECORDS")) part_records = strtoull (env, nullptr, 10);
+  if (part_records < 1024) part_records = 1024;
+  const unsigned n_parts = (unsigned) std::min<uint64_t> ((total + part_records - 1) / part_records, 256);
+  if (n_parts < 2)
+    return compare2_host_simple (records_a, n_a, records_b, n_b, word_length, ops, rule, cutoff, count_override, subtract, countonly,
+                                 out_records, out_capacity, n_out, total_out);
+  return compare2_host_pipelined (static_cast<const unsigned char *> (records_a), n_a, static_cast<const unsigned char *> (records_b), n_b,
+                                  word_length, ops, rule, cutoff, count_override, subtract, countonly,
+                                  out_records, out_capacity, n_out, total_out, n_parts);
 }
 
 // ------------------------------------------------------------------ sharding plan (host only)

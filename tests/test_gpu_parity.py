@@ -305,6 +305,23 @@ def test_host_to_host_path_and_caller_buffers(g, oracle):
     assert n_out[0] == want["union"].n_words and t_out[1] == want["intrsec"].total_count
     assert ou[:n_out[0]].tobytes() == want["union"].records().tobytes()
     assert oi[:n_out[1]].tobytes() == want["intrsec"].records().tobytes()
+    # the pipelined variant (key-range parts, H2D || merge || D2H on three streams): force many small parts
+    os.environ["GT4GPU_HOST_PART_RECORDS"] = "30000"
+    try:
+        want4 = oracle.compare2(sa, sb, union=True, intrsec=True, diff=True, ddiff=True, cutoff=2, rule="max")
+        outs = [np.zeros(len(a[0]) + len(b[0]), dtype=api.RECORD) for _ in range(4)]
+        n_out, t_out = api.compare2_host_records(sa.records(), sb.records(), 25, 15, rule="max", cutoff=2, out_records=outs)
+        for q, s_ in enumerate(STREAMS):
+            assert (n_out[q], t_out[q]) == (want4[s_].n_words, want4[s_].total_count), s_
+            assert outs[q][:n_out[q]].tobytes() == want4[s_].records().tobytes(), s_
+        n_out, t_out = api.compare2_host_records(sa.records(), sb.records(), 25, api.OP_DIFF, cutoff=2, countonly=1)
+        w1 = oracle.compare2(sa, sb, diff=True, cutoff=2)["diff1"]
+        assert (n_out[2], t_out[2]) == (w1.n_words, w1.total_count)
+        with pytest.raises(g.GT4GPUError) as ei:
+            api.compare2_host_records(sa.records(), sb.records(), 25, api.OP_UNION, out_records=[outs[0][:1000], None, None, None])
+        assert ei.value.code == 5
+    finally:
+        del os.environ["GT4GPU_HOST_PART_RECORDS"]
     # caller-owned device buffers (torch tensors), then a too-small one
     la, lb = g.WordList.from_arrays(*a, 25), g.WordList.from_arrays(*b, 25)
     cap = len(a[0]) + len(b[0])
