@@ -281,6 +281,7 @@ def run_gt4gpu_arm(args):
     m_local, pa, pb = universe_for(args.n_per_list, args.overlap)
     universe = m_local * world
     (wa, ca), (wb, cb) = synth.pair_torch(42, args.k, universe, rank * m_local, (rank + 1) * m_local, pa, pb, device="cuda")
+    torch.cuda.synchronize()
     na, nb = wa.numel(), wb.numel()
     la = g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), na, args.k, keepalive=(wa, ca))
     lb = g.WordList.from_device(wb.data_ptr(), cb.data_ptr(), nb, args.k, keepalive=(wb, cb))

@@ -49,9 +49,20 @@ def init(device: int = -1) -> None:
     _check(_lib.load().gt4gpu_init(device))
 
 
-def set_stream(cuda_stream: int) -> None:
-    """Launch on an external cudaStream_t (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
-    _check(_lib.load().gt4gpu_set_stream(C.c_void_p(cuda_stream)))
+CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy: the handle that names the default stream explicitly
+
+
+def set_stream(cuda_stream: int | None) -> None:
+    """Launch on an external cudaStream_t, e.g. ``torch.cuda.current_stream().cuda_stream``.
+
+    torch reports its default stream as 0; that is translated to ``cudaStreamLegacy`` so that the library's
+    kernels really are ordered with torch's (a NULL handle means "use the library's own non-blocking stream"
+    in the C ABI, which is NOT ordered with the default stream).  ``None`` restores the library's own stream."""
+    if cuda_stream is None:
+        handle = 0
+    else:
+        handle = cuda_stream if cuda_stream else CUDA_STREAM_LEGACY
+    _check(_lib.load().gt4gpu_set_stream(C.c_void_p(handle)))
 
 
 def set_tile(threads: int, items: int) -> None:

@@ -106,7 +106,9 @@ typedef struct gt4gpu_result {
  * library stream and memory pool.  device < 0: use the current device. */
 int gt4gpu_init (int device);
 void gt4gpu_shutdown (void);
-/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all launches. 0 restores the own stream. */
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all launches.  NULL restores the library's own
+ * non-blocking stream, which is NOT ordered with the default stream: to run on the default stream pass cudaStreamLegacy
+ * ((cudaStream_t) 0x1).  Arrays handed in through gt4gpu_list_from_device must be complete on the launch stream. */
 int gt4gpu_set_stream (void *cuda_stream);
 const char *gt4gpu_last_error (void);
 /* Kernel tile shape: threads per CTA and merged items per thread.  Unsupported pairs fail with GT4GPU_ERR_ARG. */
