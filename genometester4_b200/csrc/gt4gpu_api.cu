@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "../../include/gt4gpu.h"
@@ -203,6 +204,13 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
     if (v[3]) fprintf (stderr, "gt4gpu debug: look-backs %llu, mean %.0f cycles, %.2f polls, %.2f extra hops\n", v[3],
                        (double) v[0] / v[3], (double) v[1] / v[3], (double) v[2] / v[3] - 1.0);
   }
+  if (args.debug & 32) {
+    unsigned long long v[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < TOTAL_SLOTS; k++)
+      for (int r = 0; r < 3; r++) { v[2 * r] += h.totals[(args.stream0 + 1 + r) & 3][k][0]; v[2 * r + 1] += h.totals[(args.stream0 + 1 + r) & 3][k][1]; }
+    if (v[5]) fprintf (stderr, "gt4gpu debug: consumer warp cycles per tile: wait %.0f search %.0f merge %.0f scan+barrier %.0f scatter %.0f (warp-tiles %llu)\n",
+                       (double) v[0] / v[5], (double) v[1] / v[5], (double) v[2] / v[5], (double) v[3] / v[5], (double) v[4] / v[5], v[5]);
+  }
   if (h.overflow) return fail (GT4GPU_ERR_CAPACITY, "output buffer too small for the merge result");
   for (int s = 0; s < 4; s++) {
     if (!((stream_mask >> s) & 1u)) continue;
@@ -301,23 +309,74 @@ int new_list (uint64_t n, uint32_t k, gt4gpu_list **out)
   return 0;
 }
 
-// host AoS -> device SoA, chunked through a device staging buffer
+// parallel memcpy (page-cache-hot mmaps are limited by one core's page-fault + copy rate)
+static void copy_parallel (void *dst, const void *src, size_t bytes, unsigned n_threads)
+{
+  if (bytes < (8u << 20) || n_threads < 2) { memcpy (dst, src, bytes); return; }
+  std::vector<std::thread> pool;
+  const size_t piece = ((bytes / n_threads) + 4095) & ~(size_t) 4095;
+  for (unsigned t = 0; t < n_threads; t++) {
+    const size_t lo = (size_t) t * piece;
+    if (lo >= bytes) break;
+    const size_t len = std::min (piece, bytes - lo);
+    pool.emplace_back ([=] { memcpy (static_cast<unsigned char *> (dst) + lo, static_cast<const unsigned char *> (src) + lo, len); });
+  }
+  for (auto &th : pool) th.join ();
+}
+
+// host AoS -> device SoA, chunked through a device staging buffer.  Pinned sources are copied directly; pageable
+// ones (the mmap of a list file) go through two pinned bounce buffers filled by a few threads, so the copy into
+// pinned memory of chunk i+1 overlaps the H2D + de-interleave of chunk i.
 int upload_aos (const void *records, uint64_t n, uint64_t *d_words, uint32_t *d_counts)
 {
   if (n == 0) return 0;
-  const uint64_t chunk = std::min (n, STAGE_RECORDS);
-  void *stage = nullptr;
-  int rc = dev_alloc (&stage, chunk * 12);
-  if (rc) return rc;
+  cudaPointerAttributes attr;
+  bool pinned_src = false;
+  if (cudaPointerGetAttributes (&attr, records) == cudaSuccess) pinned_src = (attr.type == cudaMemoryTypeHost);
+  else cudaGetLastError ();
   const unsigned char *src = static_cast<const unsigned char *> (records);
   cudaError_t e = cudaSuccess;
-  for (uint64_t done = 0; done < n && e == cudaSuccess; done += chunk) {
-    const uint64_t m = std::min (chunk, n - done);
-    e = cudaMemcpyAsync (stage, src + done * 12, m * 12, cudaMemcpyHostToDevice, g_ctx.stream);
-    if (e == cudaSuccess) e = launch_deinterleave (stage, m, d_words + done, d_counts + done, g_ctx.stream);
+  if (pinned_src || n < (1u << 20)) {
+    const uint64_t chunk = std::min (n, STAGE_RECORDS);
+    void *stage = nullptr;
+    int rc = dev_alloc (&stage, chunk * 12);
+    if (rc) return rc;
+    for (uint64_t done = 0; done < n && e == cudaSuccess; done += chunk) {
+      const uint64_t m = std::min (chunk, n - done);
+      e = cudaMemcpyAsync (stage, src + done * 12, m * 12, cudaMemcpyHostToDevice, g_ctx.stream);
+      if (e == cudaSuccess) e = launch_deinterleave (stage, m, d_words + done, d_counts + done, g_ctx.stream);
+    }
+    dev_free (stage);
+    if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.stream);
+  } else {
+    const uint64_t chunk = std::min<uint64_t> (n, 8ull << 20);        // 96 MiB bounce buffers
+    void *stage[2] = {nullptr, nullptr}, *bounce[2] = {nullptr, nullptr};
+    cudaEvent_t done_ev[2] = {nullptr, nullptr};
+    int rc = 0;
+    for (int b = 0; b < 2 && !rc; b++) {
+      rc = dev_alloc (&stage[b], chunk * 12);
+      if (!rc && cudaMallocHost (&bounce[b], chunk * 12) != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "cudaMallocHost failed");
+      if (!rc && cudaEventCreateWithFlags (&done_ev[b], cudaEventDisableTiming) != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "cudaEventCreate failed");
+    }
+    const unsigned n_threads = std::min (8u, std::max (2u, std::thread::hardware_concurrency () / 2));
+    int b = 0;
+    for (uint64_t done = 0; done < n && !rc && e == cudaSuccess; done += chunk, b ^= 1) {
+      const uint64_t m = std::min (chunk, n - done);
+      if (done >= 2 * chunk) e = cudaEventSynchronize (done_ev[b]);     // the H2D that last read this bounce buffer
+      if (e != cudaSuccess) break;
+      copy_parallel (bounce[b], src + done * 12, m * 12, n_threads);
+      e = cudaMemcpyAsync (stage[b], bounce[b], m * 12, cudaMemcpyHostToDevice, g_ctx.stream);
+      if (e == cudaSuccess) e = launch_deinterleave (stage[b], m, d_words + done, d_counts + done, g_ctx.stream);
+      if (e == cudaSuccess) e = cudaEventRecord (done_ev[b], g_ctx.stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.stream);
+    for (int k = 0; k < 2; k++) {
+      dev_free (stage[k]);
+      if (bounce[k]) cudaFreeHost (bounce[k]);
+      if (done_ev[k]) cudaEventDestroy (done_ev[k]);
+    }
+    if (rc) return rc;
   }
-  dev_free (stage);
-  if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.stream);
   if (e != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "upload: %s", cudaGetErrorString (e));
   return 0;
 }
@@ -328,36 +387,55 @@ template <typename Sink>
 int download_aos (const uint64_t *d_words, const uint32_t *d_counts, uint64_t n, void *records, Sink sink, bool use_sink)
 {
   if (n == 0) return 0;
-  const uint64_t chunk = std::min<uint64_t> (n, use_sink ? (uint64_t) (4ull << 20) : STAGE_RECORDS);
-  void *stage = nullptr;
-  int rc = dev_alloc (&stage, chunk * 12);
-  if (rc) return rc;
-  void *pinned = nullptr;
-  if (use_sink) {
-    cudaError_t e = cudaMallocHost (&pinned, chunk * 12);
-    if (e != cudaSuccess) { dev_free (stage); return fail (GT4GPU_ERR_CUDA, "cudaMallocHost: %s", cudaGetErrorString (e)); }
+  cudaError_t e = cudaSuccess;
+  int rc = 0;
+  if (!use_sink) {
+    const uint64_t chunk = std::min (n, STAGE_RECORDS);
+    void *stage = nullptr;
+    rc = dev_alloc (&stage, chunk * 12);
+    if (rc) return rc;
+    for (uint64_t done = 0; done < n && e == cudaSuccess; done += chunk) {
+      const uint64_t m = std::min (chunk, n - done);
+      e = launch_interleave (d_words + done, d_counts + done, m, stage, g_ctx.stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync (static_cast<unsigned char *> (records) + done * 12, stage, m * 12, cudaMemcpyDeviceToHost, g_ctx.stream);
+    }
+    dev_free (stage);
+    if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.stream);
+    if (e != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "download: %s", cudaGetErrorString (e));
+    return 0;
   }
-  for (uint64_t done = 0; done < n; done += chunk) {
+  // with a sink (file writes): chunk i+1 is interleaved and copied out while the sink consumes chunk i
+  const uint64_t chunk = std::min<uint64_t> (n, 8ull << 20);
+  void *stage[2] = {nullptr, nullptr}, *pinned[2] = {nullptr, nullptr};
+  cudaEvent_t ready[2] = {nullptr, nullptr};
+  for (int b = 0; b < 2 && !rc; b++) {
+    rc = dev_alloc (&stage[b], chunk * 12);
+    if (!rc && cudaMallocHost (&pinned[b], chunk * 12) != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "cudaMallocHost failed");
+    if (!rc && cudaEventCreateWithFlags (&ready[b], cudaEventDisableTiming) != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "cudaEventCreate failed");
+  }
+  auto enqueue = [&] (uint64_t done, int b) {
     const uint64_t m = std::min (chunk, n - done);
-    cudaError_t e = launch_interleave (d_words + done, d_counts + done, m, stage, g_ctx.stream);
-    void *dst = use_sink ? pinned : static_cast<unsigned char *> (records) + done * 12;
-    if (e == cudaSuccess) e = cudaMemcpyAsync (dst, stage, m * 12, cudaMemcpyDeviceToHost, g_ctx.stream);
-    if (e == cudaSuccess && use_sink) e = cudaStreamSynchronize (g_ctx.stream);
-    if (e != cudaSuccess) {
-      dev_free (stage);
-      if (pinned) cudaFreeHost (pinned);
-      return fail (GT4GPU_ERR_CUDA, "download: %s", cudaGetErrorString (e));
-    }
-    if (use_sink) {
-      rc = sink (pinned, m * 12, done);
-      if (rc) { dev_free (stage); cudaFreeHost (pinned); return rc; }
-    }
+    e = launch_interleave (d_words + done, d_counts + done, m, stage[b], g_ctx.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync (pinned[b], stage[b], m * 12, cudaMemcpyDeviceToHost, g_ctx.stream);
+    if (e == cudaSuccess) e = cudaEventRecord (ready[b], g_ctx.stream);
+  };
+  if (!rc) enqueue (0, 0);
+  int b = 0;
+  for (uint64_t done = 0; done < n && !rc && e == cudaSuccess; done += chunk, b ^= 1) {
+    if (done + chunk < n) enqueue (done + chunk, b ^ 1);        // its bounce buffer was consumed by the sink two rounds ago
+    if (e != cudaSuccess) break;
+    e = cudaEventSynchronize (ready[b]);
+    if (e != cudaSuccess) break;
+    rc = sink (pinned[b], std::min (chunk, n - done) * 12, done);
   }
-  dev_free (stage);
-  cudaError_t e = cudaStreamSynchronize (g_ctx.stream);
-  if (pinned) cudaFreeHost (pinned);
-  if (e != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "download: %s", cudaGetErrorString (e));
-  return 0;
+  cudaStreamSynchronize (g_ctx.stream);
+  for (int k = 0; k < 2; k++) {
+    dev_free (stage[k]);
+    if (pinned[k]) cudaFreeHost (pinned[k]);
+    if (ready[k]) cudaEventDestroy (ready[k]);
+  }
+  if (!rc && e != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "download: %s", cudaGetErrorString (e));
+  return rc;
 }
 
 int write_all (int fd, const void *buf, size_t bytes, int64_t offset)

@@ -286,10 +286,13 @@ main (int argc, const char *argv[])
   }
 
   /* from here on the GPU is needed */
+  double t_phase = now ();
   if (gt4gpu_init (-1)) {
     fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
     exit (1);
   }
+  if (debug) fprintf (stderr, "gt4gpu: device init %.3f s\n", now () - t_phase);
+  t_phase = now ();
   for (i = 0; i < nfiles; i++) {
     if (gt4gpu_list_open (fnames[i], stream, &lists[i])) {
       fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
@@ -298,6 +301,8 @@ main (int argc, const char *argv[])
     }
   }
 
+  if (debug) fprintf (stderr, "gt4gpu: lists loaded to the device in %.3f s\n", now () - t_phase);
+  t_phase = now ();
   if (nfiles == 2) {
     /* compare_wordmaps (:789-955) */
     static const char *tags[4] = { "union", "intrsec", "0_diff1", "0_diff2" };
@@ -363,6 +368,7 @@ main (int argc, const char *argv[])
       gt4gpu_result_free (&res);
     }
   }
+  if (debug) fprintf (stderr, "gt4gpu: merge + output %.3f s\n", now () - t_phase);
   for (i = 0; i < nfiles; i++) gt4gpu_list_close (lists[i]);
   gt4gpu_shutdown ();
   return v ? 1 : 0;

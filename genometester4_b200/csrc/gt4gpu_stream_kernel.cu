@@ -102,24 +102,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx (uint64_t *bar, uint32_t b
   asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ bool mbar_try_wait (uint64_t *bar, uint32_t parity)
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out, so a
+// waiting warp does not burn issue slots polling
+__device__ __forceinline__ bool mbar_try_wait (uint64_t *bar, uint32_t parity, uint32_t hint_ns)
 {
   uint32_t ok;
-  asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok) : "r"(smem_u32 (bar)), "r"(parity) : "memory");
+  asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(smem_u32 (bar)), "r"(parity), "r"(hint_ns) : "memory");
   return ok != 0;
 }
 
 __device__ __forceinline__ void mbar_wait (uint64_t *bar, uint32_t parity)
 {
-  while (!mbar_try_wait (bar, parity)) { }
+  while (!mbar_try_wait (bar, parity, 2000u)) { }
 }
 
-// helper warps (producer, look-back, store) poll with a back-off so that their spinning does not take issue
-// slots from the consumer warps
+// helper warps (producer, look-back, store) can afford to sleep longer
 __device__ __forceinline__ void mbar_wait_relaxed (uint64_t *bar, uint32_t parity)
 {
-  while (!mbar_try_wait (bar, parity)) __nanosleep (128);
+  while (!mbar_try_wait (bar, parity, 20000u)) { }
 }
 
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
@@ -136,6 +137,12 @@ __device__ __forceinline__ void prefetch_l2 (const void *p, uint64_t bytes)
   const uintptr_t hi = ((uintptr_t) p + bytes) & ~(uintptr_t) 15;
   if (hi > lo) asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(lo), "r"((uint32_t) (hi - lo)) : "memory");
 }
+
+// The compacted records of a tile are written by the consumers at data-dependent positions (thread t starts at
+// its exclusive prefix: neighbouring lanes are ~0.75 VT records apart) and read back linearly by the store warps.
+// XOR-ing bits 4..7 of the position into bits 0..3 keeps every aligned group of 16 records a permutation of itself
+// (linear reads stay conflict-free) while positions that differ by a multiple of 16 no longer share a bank.
+__device__ __forceinline__ int swz (int pos) { return pos ^ ((pos >> 4) & 15); }
 
 __device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init () { asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -290,7 +297,7 @@ setop2_stream_kernel (const TileArgs args)
     uint64_t nxt_lo = 0, nxt_hi = 0;
     if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
     // L2 prefetch of the tiles the grid will claim about two rounds from now (co-ranks loaded one iteration early)
-    const uint64_t pf_dist = (uint64_t) ((args.debug >> 4) ? (args.debug >> 4) : 1) * gridDim.x;
+    const uint64_t pf_dist = gridDim.x;
     uint64_t pf_tile = nxt + pf_dist, pf_lo = 0, pf_hi = 0;
     if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
     int s = 0;
@@ -445,27 +452,29 @@ setop2_stream_kernel (const TileArgs args)
       const int cnt = s_mail[s].cnt;
       const uint64_t *sk = stage_keys (s);
       const uint32_t *sc = stage_cnts (s);
-      if (base + (uint64_t) cnt <= args.out_capacity[stream]) {
+      if (args.debug & 8) {
+        // experiment: no stores
+      } else if (base + (uint64_t) cnt <= args.out_capacity[stream]) {
         uint64_t *ow = args.out_words[stream] + base;
         uint32_t *oc = args.out_counts[stream] + base;
         int x = st_tid;
         for (; x + 7 * ST_THREADS < cnt; x += 8 * ST_THREADS) {
           uint64_t k[8];
 #pragma unroll
-          for (int r = 0; r < 8; r++) k[r] = sk[x + r * ST_THREADS];
+          for (int r = 0; r < 8; r++) k[r] = sk[swz (x + r * ST_THREADS)];
 #pragma unroll
           for (int r = 0; r < 8; r++) ow[x + r * ST_THREADS] = k[r];
         }
-        for (; x < cnt; x += ST_THREADS) ow[x] = sk[x];
+        for (; x < cnt; x += ST_THREADS) ow[x] = sk[swz (x)];
         x = st_tid;
         for (; x + 7 * ST_THREADS < cnt; x += 8 * ST_THREADS) {
           uint32_t c[8];
 #pragma unroll
-          for (int r = 0; r < 8; r++) c[r] = sc[x + r * ST_THREADS];
+          for (int r = 0; r < 8; r++) c[r] = sc[swz (x + r * ST_THREADS)];
 #pragma unroll
           for (int r = 0; r < 8; r++) oc[x + r * ST_THREADS] = c[r];
         }
-        for (; x < cnt; x += ST_THREADS) oc[x] = sc[x];
+        for (; x < cnt; x += ST_THREADS) oc[x] = sc[swz (x)];
       } else if (st_tid == 0) {
         args.hdr->overflow = 1u;
       }
@@ -482,7 +491,10 @@ setop2_stream_kernel (const TileArgs args)
   unsigned long long acc_n = 0, acc_sum = 0;   // this thread's share of the header totals
   int s = 0, n_end = 0;
   uint32_t ph = 0;
+  const bool prof = (args.debug & 32) != 0;
+  long long t_wait = 0, t_search = 0, t_merge = 0, t_scan = 0, t_scatter = 0, n_tiles_done = 0;
   for (uint32_t it = 0;; it++) {
+    const long long c0 = prof ? clock64 () : 0;
     mbar_wait (&bar_split[s], ph);
     mbar_wait (&bar_full[s], ph);        // already complete; observed directly for the TMA-written data
     const StageMeta m = s_meta[s];
@@ -509,7 +521,9 @@ setop2_stream_kernel (const TileArgs args)
     const uint32_t *cb = sc + m.cb;
     const int n_tile = m.na + m.nb;
     const int d0 = (tid * VT < n_tile) ? tid * VT : n_tile;
+    const long long c1 = prof ? clock64 () : 0;
     const int i0 = merge_path_window<int> (ka, m.na, kb, m.nb, d0, s_split[s][tid / GROUP], s_split[s][tid / GROUP + 1]);
+    const long long c2 = prof ? clock64 () : 0;
 
     uint64_t o_key[VT];
     uint32_t o_freq[VT];
@@ -527,6 +541,8 @@ setop2_stream_kernel (const TileArgs args)
 #pragma unroll
     for (int sl = 0; sl < VT; sl++) acc_sum += ((mask >> sl) & 1u) ? o_freq[sl] : 0u;
 
+    const long long c3 = prof ? clock64 () : 0;
+    if (prof) { t_wait += c1 - c0; t_search += c2 - c1; t_merge += c3 - c2; n_tiles_done += 1; }
     if (COUNT_ONLY) {
       __syncwarp ();
       if (lane == 0) mbar_arrive (&bar_empty[s]);    // only generic reads touched the stage
@@ -543,13 +559,18 @@ setop2_stream_kernel (const TileArgs args)
     }
     if (lane == 31) s_wcnt[it & 1][warp] = incl;
     consumer_sync<NC> ();           // also: every consumer is done reading this stage's inputs
-    int warp_prefix = 0, tile_cnt = 0;
+    const long long c4 = prof ? clock64 () : 0;
+    // prefix over the (at most 32) warp totals with one more shuffle scan instead of a loop per thread
+    static_assert (NWARPS <= 32, "one lane per consumer warp");
+    const int wv = (lane < NWARPS) ? s_wcnt[it & 1][lane] : 0;
+    int wincl = wv;
 #pragma unroll
-    for (int w = 0; w < NWARPS; w++) {
-      const int v = s_wcnt[it & 1][w];
-      if (w < warp) warp_prefix += v;
-      tile_cnt += v;
+    for (int off = 1; off < NWARPS; off <<= 1) {
+      const int t = __shfl_up_sync (0xffffffffu, wincl, off);
+      if (lane >= off) wincl += t;
     }
+    const int tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
+    const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
     if (tid == 0) {
       s_mail[s].tile = m.tile;
       s_mail[s].cnt = tile_cnt;
@@ -561,14 +582,23 @@ setop2_stream_kernel (const TileArgs args)
 #pragma unroll
     for (int sl = 0; sl < VT; sl++) {
       if ((mask >> sl) & 1u) {
-        sk[pos] = o_key[sl];
-        sc[pos] = o_freq[sl];
+        sk[swz (pos)] = o_key[sl];
+        sc[swz (pos)] = o_freq[sl];
         pos += 1;
       }
     }
     __syncwarp ();
     if (lane == 0) mbar_arrive (&bar_comp[s]);
+    if (prof) { const long long c5 = clock64 (); t_scan += c4 - c3; t_scatter += c5 - c4; }
     if (++s == STAGES) { s = 0; ph ^= 1u; }
+  }
+  if (prof && lane == 0) {       // experiments: per-phase cycles of the consumer warps in the unused totals rows
+    unsigned long long *row = args.hdr->totals[(stream + 1) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
+    atomicAdd (row, (unsigned long long) t_wait); atomicAdd (row + 1, (unsigned long long) t_search);
+    row = args.hdr->totals[(stream + 2) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
+    atomicAdd (row, (unsigned long long) t_merge); atomicAdd (row + 1, (unsigned long long) t_scan);
+    row = args.hdr->totals[(stream + 3) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
+    atomicAdd (row, (unsigned long long) t_scatter); atomicAdd (row + 1, (unsigned long long) n_tiles_done);
   }
 
   // header totals: one pair of atomics per CTA
@@ -631,7 +661,7 @@ cudaError_t launch_stream_fast (const TileArgs &args, int fast, int sm_count, cu
 }  // namespace
 
 // supported (consumer threads, items per thread, stages) triples; the stage count is fixed per shape by shared memory
-#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 3) X (256, 11, 3) X (512, 7, 5) X (512, 8, 4) X (512, 9, 4) X (512, 10, 3) X (512, 11, 3) X (256, 8, 4) X (256, 10, 3)
+#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 4) X (256, 11, 3) X (512, 7, 5) X (512, 9, 4) X (512, 11, 3)
 
 bool stream_shape_supported (int consumers, int items)
 {
