@@ -111,3 +111,37 @@ def pair_torch(seed: int, k: int, universe: int, u0: int, u1: int, p_a_only: flo
 def to_numpy_u(words_t, counts_t):
     """torch (int64, int32) bit patterns -> numpy (uint64, uint32)."""
     return words_t.cpu().numpy().view(np.uint64), counts_t.cpu().numpy().view(np.uint32)
+
+
+# ------------------------------------------------------------------ N lists over one shared universe (config 5)
+
+def list_numpy(seed: int, k: int, universe: int, u0: int, u1: int, list_id: int, p_member: float):
+    """List `list_id` of a family drawn from ONE universe (same keys, independent membership and counts)."""
+    g = gap(k, universe)
+    u = np.arange(u0, u1, dtype=np.uint64)
+    s = np.uint64(seed & 0xFFFFFFFFFFFFFFFF)
+    salt = np.uint64((0xD1B54A32D192ED03 * (list_id + 1)) & 0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        key = u * np.uint64(g) + (_mix_np(u ^ s ^ np.uint64(SALT_KEY)) >> np.uint64(1)) % np.uint64(g)
+    r = (_mix_np(u ^ s ^ salt ^ np.uint64(SALT_MEMBER)) >> np.uint64(40)).astype(np.int64)
+    member = r < int(p_member * (1 << 24))
+    c = _counts_np(_mix_np(u ^ s ^ salt ^ np.uint64(SALT_CA)))
+    return key[member], c[member]
+
+
+def list_torch(seed: int, k: int, universe: int, u0: int, u1: int, list_id: int, p_member: float, device="cuda", chunk: int = 1 << 26):
+    import torch
+    g = gap(k, universe)
+    s = _s64(seed)
+    salt = _s64(0xD1B54A32D192ED03 * (list_id + 1))
+    thr = int(p_member * (1 << 24))
+    ws, cs = [], []
+    for c0 in range(u0, u1, chunk):
+        c1 = min(c0 + chunk, u1)
+        u = torch.arange(c0, c1, dtype=torch.int64, device=device)
+        key = u * g + torch.remainder(_lsr(_mix_t(u ^ s ^ _s64(SALT_KEY)), 1), g)
+        member = _lsr(_mix_t(u ^ s ^ salt ^ _s64(SALT_MEMBER)), 40) < thr
+        c = _counts_t(_mix_t(u ^ s ^ salt ^ _s64(SALT_CA)))
+        ws.append(key[member]); cs.append(c[member])
+        del u, key, member, c
+    return (torch.cat(ws) if len(ws) != 1 else ws[0]), (torch.cat(cs) if len(cs) != 1 else cs[0])

@@ -66,7 +66,7 @@ if "5" in which:   # config 5: 8-list union (MakeUnion.pl equivalent), 8 x 5e8 o
         m = int(n_each * 3)
         lists, keep = [], []
         for j in range(8):
-            (wa, ca), _ = synth.pair_torch(5 + j, 32, m, 0, m, 1 / 3, 2 / 3)      # every list: a third of a shared universe
+            wa, ca = synth.list_torch(5, 32, m, 0, m, j, 1 / 3)                    # every list: a third of ONE shared universe
             keep.append((wa, ca))
             lists.append(g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), wa.numel(), 32))
         n_in = sum(len(l) for l in lists)
