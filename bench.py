@@ -270,9 +270,7 @@ def run_gt4gpu_arm(args):
         g.set_tile(int(nt), int(vt))
     if args.stream_shape:
         nc, vt = args.stream_shape.split("x")
-        g.set_option("stream_items", 7)
-        g.set_option("stream_consumers", int(nc))
-        g.set_option("stream_items", int(vt))
+        g.set_option("stream_shape", int(nc) * 100 + int(vt))
     if args.no_stream_kernel:
         g.set_option("use_stream_kernel", 0)
     g.set_stream(torch.cuda.current_stream().cuda_stream)

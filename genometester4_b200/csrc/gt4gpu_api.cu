@@ -613,6 +613,12 @@ int gt4gpu_set_tile (int threads, int items_per_thread)
 int gt4gpu_set_option (const char *name, int value)
 {
   if (!name) return fail (GT4GPU_ERR_ARG, "null option name");
+  if (!strcmp (name, "stream_shape")) {        // consumers * 100 + items, e.g. 51209
+    if (!stream_shape_supported (value / 100, value % 100)) return fail (GT4GPU_ERR_ARG, "stream shape %dx%d is not supported", value / 100, value % 100);
+    g_ctx.stream_consumers = value / 100;
+    g_ctx.stream_items = value % 100;
+    return 0;
+  }
   if (!strcmp (name, "stream_items")) {
     if (!stream_shape_supported (g_ctx.stream_consumers, value)) return fail (GT4GPU_ERR_ARG, "stream shape %dx%d is not supported", g_ctx.stream_consumers, value);
     g_ctx.stream_items = value;

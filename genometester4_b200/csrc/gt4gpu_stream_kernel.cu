@@ -661,7 +661,7 @@ cudaError_t launch_stream_fast (const TileArgs &args, int fast, int sm_count, cu
 }  // namespace
 
 // supported (consumer threads, items per thread, stages) triples; the stage count is fixed per shape by shared memory
-#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 4) X (256, 11, 3) X (512, 7, 5) X (512, 9, 4) X (512, 11, 3)
+#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 4) X (256, 11, 3) X (384, 9, 5) X (384, 11, 4) X (512, 7, 5) X (512, 9, 4) X (512, 11, 3)
 
 bool stream_shape_supported (int consumers, int items)
 {

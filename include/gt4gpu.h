@@ -113,8 +113,8 @@ int gt4gpu_set_stream (void *cuda_stream);
 const char *gt4gpu_last_error (void);
 /* Kernel tile shape: threads per CTA and merged items per thread.  Unsupported pairs fail with GT4GPU_ERR_ARG. */
 int gt4gpu_set_tile (int threads, int items_per_thread);
-/* Tuning knobs: "stream_consumers" (256 or 512 consumer threads per CTA of the single-output kernel),
- * "stream_items" (its merged items per thread: 7, 9 or 11) and
+/* Tuning knobs: "stream_shape" (consumer threads per CTA * 100 + merged items per thread of the single-output kernel,
+ * e.g. 51209; also settable one at a time as "stream_consumers" / "stream_items") and
  * "use_stream_kernel" (0 routes single-output merges through the multi-output tile kernel as well). */
 int gt4gpu_set_option (const char *name, int value);
 /* Device time of the most recent merge call on this thread, from CUDA events on the launch stream:

@@ -10,7 +10,7 @@ from genometester4_b200 import synth
 n = float(sys.argv[1]); nc, vt = (int(x) for x in sys.argv[2].split("x")); co = int(sys.argv[3])
 op = sys.argv[4] if len(sys.argv) > 4 else "union"
 g.init(0); g.set_stream(torch.cuda.current_stream().cuda_stream)
-g.set_option("stream_items", 7); g.set_option("stream_consumers", nc); g.set_option("stream_items", vt)
+g.set_option("stream_shape", nc * 100 + vt)
 m = int(round(1.5 * n))
 (wa, ca), (wb, cb) = synth.pair_torch(42, 25, m, 0, m, 1 / 3, 1 / 3)
 na, nb = wa.numel(), wb.numel()

@@ -15,7 +15,7 @@ na, nb = wa.numel(), wb.numel()
 la = g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), na, 25); lb = g.WordList.from_device(wb.data_ptr(), cb.data_ptr(), nb, 25)
 ow = torch.empty(na + nb, dtype=torch.int64, device="cuda"); oc = torch.empty(na + nb, dtype=torch.int32, device="cuda")
 for nc, vt in shapes:
-    g.set_option("stream_items", 7); g.set_option("stream_consumers", nc); g.set_option("stream_items", vt)
+    g.set_option("stream_shape", nc * 100 + vt)
     for co in (0, 1):
         ms = []
         for it in range(6):

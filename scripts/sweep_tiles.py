@@ -30,9 +30,7 @@ for op, kw, name in (("union", dict(find_union=1), "union"), ("intersect", dict(
         for nt, vt in shapes:
             if isinstance(nt, str):
                 g.set_option("use_stream_kernel", 1)
-                g.set_option("stream_items", 7)
-                g.set_option("stream_consumers", int(nt[1:]))
-                g.set_option("stream_items", vt)
+                g.set_option("stream_shape", int(nt[1:]) * 100 + vt)
             else:
                 g.set_option("use_stream_kernel", 0)
                 g.set_tile(nt, vt)

@@ -109,15 +109,13 @@ def test_medium_lists_every_tile_shape(g, oracle, shape):
     g.set_tile(256, 9)
 
 
-@pytest.mark.parametrize("shape", [(256, 7), (256, 9), (256, 11), (512, 7), (512, 9), (512, 11)])
+@pytest.mark.parametrize("shape", [(256, 7), (256, 9), (256, 11), (384, 9), (384, 11), (512, 7), (512, 9), (512, 11)])
 def test_stream_kernel_every_shape_rule_and_semantics(g, oracle, shape):
     """The persistent single-output kernel (TMA-staged, warp-specialised): every items-per-thread
     variant x every rule (fast paths and the generic path) x pair / N-list semantics, on inputs of
     hundreds of tiles with odd sizes so that slices start at every 16-byte misalignment."""
     items = shape
-    g.set_option("stream_items", 7)
-    g.set_option("stream_consumers", shape[0])
-    g.set_option("stream_items", shape[1])
+    g.set_option("stream_shape", shape[0] * 100 + shape[1])
     g.set_option("use_stream_kernel", 1)
     try:
         for seed, (na, nb, both), kind in ((11, (300_001, 250_003, 120_000), "tail"), (12, (65_537, 65_539, 65_537), "small"),
@@ -143,9 +141,7 @@ def test_stream_kernel_every_shape_rule_and_semantics(g, oracle, shape):
                     w, c = r.to_host()
                     assert np.array_equal(w, want_du.words) and np.array_equal(c, want_du.counts), (items, seed, rule, cutoff, "du")
     finally:
-        g.set_option("stream_items", 7)
-        g.set_option("stream_consumers", 512)
-        g.set_option("stream_items", 9)
+        g.set_option("stream_shape", 51209)
 
 
 def test_stream_kernel_misaligned_device_views(g, oracle):
