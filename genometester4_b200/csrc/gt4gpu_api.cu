@@ -127,9 +127,11 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   const uint64_t total = a.n + b.n;
   const int n_req = __builtin_popcount (stream_mask);
   if (n_req == 0) return fail (GT4GPU_ERR_ARG, "no output stream requested");
-  const int ns = (n_req == 1) ? 1 : 4;
+  // Several outputs: one pass of the single-output kernel per output beats the fused multi-output kernel by ~2x
+  // (measured, profiles/README.md), so the fused kernel is only used when the stream kernel is switched off.
   const TileShape shape = g_ctx.shape;
-  const bool use_stream = (n_req == 1) && g_ctx.use_stream;
+  const bool use_stream = g_ctx.use_stream != 0;
+  const int ns = (n_req == 1 || use_stream) ? 1 : 4;
   const uint64_t tile = use_stream ? (uint64_t) g_ctx.stream_consumers * g_ctx.stream_items : (uint64_t) shape.threads * shape.items;
   const uint64_t n_tiles = (total + tile - 1) / tile;
   cudaStream_t st = g_ctx.stream;
@@ -180,8 +182,25 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   CU (cudaEventRecord (tl_ev[0], st));
   CU (launch_partition (a.words, a.n, b.words, b.n, (uint32_t) tile, n_tiles, part, st));
   CU (cudaEventRecord (tl_ev[1], st));
-  if (use_stream) CU (launch_setop2_stream (args, g_ctx.stream_consumers, g_ctx.stream_items, countonly, g_ctx.sm_count, st));
-  else CU (launch_setop2 (args, shape, ns, countonly, st));
+  uint32_t n_launches = 1;
+  if (use_stream) {
+    bool first = true;
+    for (int s = 0; s < 4; s++) {
+      if (!((stream_mask >> s) & 1u)) continue;
+      if (!first) {       // same co-ranks, fresh ticket and look-back descriptors
+        CU (cudaMemsetAsync (&args.hdr->ticket, 0, sizeof (uint32_t), st));
+        if (desc_bytes) CU (cudaMemsetAsync (args.desc, 0, desc_bytes, st));
+      }
+      first = false;
+      args.stream0 = s;
+      args.p.ops = 1u << s;
+      CU (launch_setop2_stream (args, g_ctx.stream_consumers, g_ctx.stream_items, countonly, g_ctx.sm_count, st));
+      n_launches += 1;
+    }
+  } else {
+    CU (launch_setop2 (args, shape, ns, countonly, st));
+    n_launches += 1;
+  }
   CU (cudaEventRecord (tl_ev[2], st));
 
   CallHeader h;
@@ -193,7 +212,7 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   tl_ms_partition += ms;
   CU (cudaEventElapsedTime (&ms, tl_ev[1], tl_ev[2]));
   tl_ms_merge += ms;
-  tl_launches += 2;
+  tl_launches += n_launches;
 
   if (args.debug & 2) {
     unsigned long long v[4] = {0, 0, 0, 0};

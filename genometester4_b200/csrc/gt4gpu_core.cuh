@@ -132,7 +132,8 @@ enum FastPath : int {
   FAST_I_MIN = 2,     // SEM_PAIR, intersection, rule min
   FAST_D_SUB = 3,     // SEM_PAIR, diff1, rule subtract, no -du
   FAST_NU_ADD = 4,    // N-list union node, rule add
-  FAST_NI_MIN = 5     // N-list intersection link, rule min
+  FAST_NI_MIN = 5,    // N-list intersection link, rule min
+  FAST_D2_SUB = 6     // SEM_PAIR, diff2 (list 2 minus list 1), rule subtract
 };
 
 GT4_HD int select_fast_path (const SetOpParams &p, int stream)
@@ -141,6 +142,7 @@ GT4_HD int select_fast_path (const SetOpParams &p, int stream)
     if (stream == 0 && p.rule[0] == RULE_ADD) return FAST_U_ADD;
     if (stream == 1 && p.rule[1] == RULE_MIN) return FAST_I_MIN;
     if (stream == 2 && p.rule[2] == RULE_SUBTRACT && !p.subtract) return FAST_D_SUB;
+    if (stream == 3 && p.rule[3] == RULE_SUBTRACT) return FAST_D2_SUB;
     return FAST_GENERIC;
   }
   if (stream != 0) return FAST_GENERIC;
@@ -164,6 +166,10 @@ GT4_HD bool eval_fast (const SetOpParams &p, int stream, uint32_t c1, uint32_t c
     const uint32_t f2 = in_b ? c2 : 0u;
     f = (c1 > f2) ? c1 - f2 : 0u;
     return in_a && c1 >= c && f2 < c && f != 0u;
+  } else if (FAST == FAST_D2_SUB) {
+    const uint32_t f1 = in_a ? c1 : 0u;
+    f = (c2 > f1) ? c2 - f1 : 0u;
+    return in_b && c2 >= c && f1 < c && f != 0u;
   } else if (FAST == FAST_NU_ADD) {
     f = (in_a ? c1 : 0u) + (in_b ? c2 : 0u);
     return p.sem == SEM_NUNION_PARTIAL || f >= c;

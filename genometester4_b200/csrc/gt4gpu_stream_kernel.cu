@@ -654,6 +654,7 @@ cudaError_t launch_stream_fast (const TileArgs &args, int fast, int sm_count, cu
   case FAST_D_SUB:  return launch_stream_one<NC, VT, S, FAST_D_SUB, CO> (args, sm_count, st);
   case FAST_NU_ADD: return launch_stream_one<NC, VT, S, FAST_NU_ADD, CO> (args, sm_count, st);
   case FAST_NI_MIN: return launch_stream_one<NC, VT, S, FAST_NI_MIN, CO> (args, sm_count, st);
+  case FAST_D2_SUB: return launch_stream_one<NC, VT, S, FAST_D2_SUB, CO> (args, sm_count, st);
   default:          return launch_stream_one<NC, VT, S, FAST_GENERIC, CO> (args, sm_count, st);
   }
 }

@@ -111,7 +111,7 @@ static uint64_t check_fast (const SetOpParams &p, int stream)
 extern "C" uint64_t emu_check_fast_paths (void)
 {
   static const uint32_t cutoffs[] = {0u, 1u, 2u, 5u, 100u, 0x80000000u, 0xffffffffu};
-  uint64_t bad = 0, selected[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t bad = 0, selected[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int sem = 0; sem < 5; sem++) for (int rule = 0; rule < 8; rule++) for (int sub = 0; sub < 2; sub++)
     for (uint32_t cutoff : cutoffs) for (int stream = 0; stream < 4; stream++) {
       SetOpParams p;
@@ -126,9 +126,10 @@ extern "C" uint64_t emu_check_fast_paths (void)
       case FAST_D_SUB: bad += check_fast<FAST_D_SUB> (p, stream); break;
       case FAST_NU_ADD: bad += check_fast<FAST_NU_ADD> (p, stream); break;
       case FAST_NI_MIN: bad += check_fast<FAST_NI_MIN> (p, stream); break;
+      case FAST_D2_SUB: bad += check_fast<FAST_D2_SUB> (p, stream); break;
       default: bad += check_fast<FAST_GENERIC> (p, stream); break;
       }
     }
-  for (int f = 1; f < 6; f++) if (!selected[f]) bad += 1000000;   // every fast path must be reachable
+  for (int f = 1; f < 7; f++) if (!selected[f]) bad += 1000000;   // every fast path must be reachable
   return bad;
 }

@@ -88,8 +88,10 @@ def test_pair_full_matrix_vs_oracle(g, pair_lists, oracle):
 
 @pytest.mark.parametrize("shape", [(128, 15), (128, 17), (256, 7), (256, 9), (256, 11), (256, 15), (512, 7), (512, 9)])
 def test_medium_lists_every_tile_shape(g, oracle, shape):
-    """Hundreds of tiles: partition, look-back offsets and compaction across CTAs."""
+    """The one-CTA-per-tile kernel (fused multi-output; reached with use_stream_kernel=0): hundreds of tiles,
+    partition, look-back offsets and compaction across CTAs."""
     g.set_tile(*shape)
+    g.set_option("use_stream_kernel", 0)
     for seed, (na, nb, both), kind in ((1, (300_000, 250_000, 120_000), "tail"), (2, (200_000, 200_000, 200_000), "small"),
                                        (3, (1, 400_000, 1), "tail"), (4, (150_000, 10, 0), "huge")):
         a, b = make_pair(seed, na, nb, both, 25, kind)
@@ -107,6 +109,7 @@ def test_medium_lists_every_tile_shape(g, oracle, shape):
             co = g.compare_wordmaps(la, lb, cutoff=3, countonly=1, **kw)[s]
             assert (co.n_words, co.total_count) == (want[s].n_words, want[s].total_count)
     g.set_tile(256, 9)
+    g.set_option("use_stream_kernel", 1)
 
 
 @pytest.mark.parametrize("shape", [(256, 7), (256, 9), (256, 11), (384, 9), (384, 11), (512, 7), (512, 9), (512, 11)])
