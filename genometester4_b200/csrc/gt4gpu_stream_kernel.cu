@@ -138,12 +138,6 @@ __device__ __forceinline__ void prefetch_l2 (const void *p, uint64_t bytes)
   if (hi > lo) asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(lo), "r"((uint32_t) (hi - lo)) : "memory");
 }
 
-// The compacted records of a tile are written by the consumers at data-dependent positions (thread t starts at
-// its exclusive prefix: neighbouring lanes are ~0.75 VT records apart) and read back linearly by the store warps.
-// XOR-ing bits 4..7 of the position into bits 0..3 keeps every aligned group of 16 records a permutation of itself
-// (linear reads stay conflict-free) while positions that differ by a multiple of 16 no longer share a bank.
-__device__ __forceinline__ int swz (int pos) { return pos ^ ((pos >> 4) & 15); }
-
 __device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init () { asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 template <int NC>
@@ -461,20 +455,20 @@ setop2_stream_kernel (const TileArgs args)
         for (; x + 7 * ST_THREADS < cnt; x += 8 * ST_THREADS) {
           uint64_t k[8];
 #pragma unroll
-          for (int r = 0; r < 8; r++) k[r] = sk[swz (x + r * ST_THREADS)];
+          for (int r = 0; r < 8; r++) k[r] = sk[x + r * ST_THREADS];
 #pragma unroll
           for (int r = 0; r < 8; r++) ow[x + r * ST_THREADS] = k[r];
         }
-        for (; x < cnt; x += ST_THREADS) ow[x] = sk[swz (x)];
+        for (; x < cnt; x += ST_THREADS) ow[x] = sk[x];
         x = st_tid;
         for (; x + 7 * ST_THREADS < cnt; x += 8 * ST_THREADS) {
           uint32_t c[8];
 #pragma unroll
-          for (int r = 0; r < 8; r++) c[r] = sc[swz (x + r * ST_THREADS)];
+          for (int r = 0; r < 8; r++) c[r] = sc[x + r * ST_THREADS];
 #pragma unroll
           for (int r = 0; r < 8; r++) oc[x + r * ST_THREADS] = c[r];
         }
-        for (; x < cnt; x += ST_THREADS) oc[x] = sc[swz (x)];
+        for (; x < cnt; x += ST_THREADS) oc[x] = sc[x];
       } else if (st_tid == 0) {
         args.hdr->overflow = 1u;
       }
@@ -582,8 +576,8 @@ setop2_stream_kernel (const TileArgs args)
 #pragma unroll
     for (int sl = 0; sl < VT; sl++) {
       if ((mask >> sl) & 1u) {
-        sk[swz (pos)] = o_key[sl];
-        sc[swz (pos)] = o_freq[sl];
+        sk[pos] = o_key[sl];
+        sc[pos] = o_freq[sl];
         pos += 1;
       }
     }
