@@ -287,6 +287,18 @@ setop2_stream_kernel (const TileArgs args)
     if (lane != 0) return;
     const uint64_t total = args.na + args.nb;
     const uint64_t n_tiles = args.n_tiles;
+    // 16-byte aligned interior [lo, hi) of the four input arrays
+    uintptr_t lim[8];
+    {
+      const uintptr_t lo[4] = {(uintptr_t) args.a_words, (uintptr_t) args.b_words, (uintptr_t) args.a_counts, (uintptr_t) args.b_counts};
+      const uintptr_t hi[4] = {(uintptr_t) (args.a_words + args.na), (uintptr_t) (args.b_words + args.nb),
+                               (uintptr_t) (args.a_counts + args.na), (uintptr_t) (args.b_counts + args.nb)};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        lim[2 * q] = (lo[q] + 15) & ~(uintptr_t) 15;
+        lim[2 * q + 1] = hi[q] & ~(uintptr_t) 15;
+      }
+    }
     uint64_t nxt = atomicAdd (&args.hdr->ticket, 1u);
     uint64_t nxt_lo = 0, nxt_hi = 0;
     if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
@@ -335,7 +347,9 @@ setop2_stream_kernel (const TileArgs args)
       uint64_t *sk = stage_keys (s);
       uint32_t *sc = stage_cnts (s);
 
-      // byte ranges to fetch, widened to 16-byte boundaries (TMA bulk copies need aligned address and size)
+      // Byte ranges to stage.  A block is laid out from the 16-byte boundary below its first byte to the one above
+      // its last byte (TMA bulk copies need 16-byte aligned addresses and sizes).  Nothing outside the arrays is
+      // ever read: see the edge case below.
       const uintptr_t ak0 = (uintptr_t) (args.a_words + a_lo - halo), ak1 = (uintptr_t) (args.a_words + a_hi);
       const uintptr_t bk0 = (uintptr_t) (args.b_words + b_lo), bk1 = (uintptr_t) (args.b_words + b_hi + peek);
       const uintptr_t ac0 = (uintptr_t) (args.a_counts + a_lo - halo), ac1 = (uintptr_t) (args.a_counts + a_hi);
@@ -357,11 +371,49 @@ setop2_stream_kernel (const TileArgs args)
       m.flags = halo | (peek << 1);
       s_meta[s] = m;
 
-      mbar_arrive_expect_tx (&bar_full[s], ak_bytes + bk_bytes + ac_bytes + bc_bytes);
-      if (ak_bytes) bulk_g2s (sk, (const void *) ak0a, ak_bytes, &bar_full[s]);
-      if (bk_bytes) bulk_g2s (sk + (ak_bytes >> 3), (const void *) bk0a, bk_bytes, &bar_full[s]);
-      if (ac_bytes) bulk_g2s (sc, (const void *) ac0a, ac_bytes, &bar_full[s]);
-      if (bc_bytes) bulk_g2s (sc + (ac_bytes >> 2), (const void *) bc0a, bc_bytes, &bar_full[s]);
+      unsigned char *skb = reinterpret_cast<unsigned char *> (sk), *scb = reinterpret_cast<unsigned char *> (sc);
+      const bool interior = ak0a >= lim[0] && ak0a + ak_bytes <= lim[1] && bk0a >= lim[2] && bk0a + bk_bytes <= lim[3] &&
+                            ac0a >= lim[4] && ac0a + ac_bytes <= lim[5] && bc0a >= lim[6] && bc0a + bc_bytes <= lim[7];
+      if (interior) {     // the common case: four aligned bulk copies
+        mbar_arrive_expect_tx (&bar_full[s], ak_bytes + bk_bytes + ac_bytes + bc_bytes);
+        if (ak_bytes) bulk_g2s (skb, (const void *) ak0a, ak_bytes, &bar_full[s]);
+        if (bk_bytes) bulk_g2s (skb + ak_bytes, (const void *) bk0a, bk_bytes, &bar_full[s]);
+        if (ac_bytes) bulk_g2s (scb, (const void *) ac0a, ac_bytes, &bar_full[s]);
+        if (bc_bytes) bulk_g2s (scb + ac_bytes, (const void *) bc0a, bc_bytes, &bar_full[s]);
+      } else {
+        // a slice touches an unaligned head or tail of its array: clip the TMA part to the aligned interior and copy
+        // the rest with plain loads
+        struct Piece { uintptr_t src; uint32_t bytes; unsigned char *dst; };
+        Piece tma[4];
+        uint32_t tx = 0;
+        auto plan_block = [&] (int q, uintptr_t x0, uintptr_t x1, uintptr_t x0a, uintptr_t in_lo, uintptr_t in_hi, unsigned char *block) {
+          tma[q].bytes = 0;
+          if (x1 <= x0) return;
+          uintptr_t t_lo = x0a, t_hi = (x1 + 15) & ~(uintptr_t) 15;
+          if (t_lo < in_lo) t_lo = in_lo;
+          if (t_hi > in_hi) t_hi = in_hi;
+          if (t_hi > t_lo) {
+            tma[q].src = t_lo;
+            tma[q].bytes = (uint32_t) (t_hi - t_lo);
+            tma[q].dst = block + (t_lo - x0a);
+            tx += tma[q].bytes;
+          } else {
+            t_lo = t_hi = x0;      // nothing for the TMA: copy everything by hand
+          }
+          for (uintptr_t p = x0; p < x1 && p < t_lo; p += 4)                       // unaligned head of the array
+            *reinterpret_cast<uint32_t *> (block + (p - x0a)) = *reinterpret_cast<const uint32_t *> (p);
+          for (uintptr_t p = (t_hi > x0 ? t_hi : x0); p < x1; p += 4)              // unaligned tail of the array
+            *reinterpret_cast<uint32_t *> (block + (p - x0a)) = *reinterpret_cast<const uint32_t *> (p);
+        };
+        plan_block (0, ak0, ak1, ak0a, lim[0], lim[1], skb);
+        plan_block (1, bk0, bk1, bk0a, lim[2], lim[3], skb + ak_bytes);
+        plan_block (2, ac0, ac1, ac0a, lim[4], lim[5], scb);
+        plan_block (3, bc0, bc1, bc0a, lim[6], lim[7], scb + ac_bytes);
+        mbar_arrive_expect_tx (&bar_full[s], tx);      // (release: the plain copies above are visible to whoever sees the phase complete)
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (tma[q].bytes) bulk_g2s (tma[q].dst, (const void *) tma[q].src, tma[q].bytes, &bar_full[s]);
+      }
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     return;
