@@ -39,6 +39,7 @@ struct gt4gpu_list {
 namespace {
 
 constexpr uint32_t LIST_CODE = (uint32_t) ('G' << 24 | 'T' << 16 | '4' << 8 | 'C');   // src/word-list.c:31
+constexpr uint32_t INDEX_CODE = (uint32_t) ('G' << 24 | 'T' << 16 | '4' << 8 | 'I');  // src/index-map.c:38
 constexpr uint64_t STAGE_RECORDS = 32ull << 20;   // records per AoS staging chunk (384 MiB)
 
 struct Context {
@@ -289,6 +290,68 @@ int parse_header (const unsigned char *file, uint64_t size, int mode, const char
     if (size < h.list_start + h.n_words * 12ull) return fail (GT4GPU_ERR_FORMAT, "%s: records exceed the file", path);
   }
   *out = h;
+  return 0;
+}
+
+// struct _GT4IndexHeader, src/index-map.h:69-83
+struct IndexHeader {
+  uint32_t code, version_major, version_minor, word_length;
+  uint64_t num_words, num_locations;
+  uint32_t n_file_bits, n_subseq_bits, n_pos_bits, filler0;
+  uint64_t files_start, kmers_start, locations_start;
+};
+
+// GT4I acceptance as in gt4_index_map_new (src/index-map.c:316-350); reported through a list header whose
+// count_bytes = 8 marks the 16-byte record layout (word + location offset)
+int parse_index_header (const unsigned char *file, uint64_t size, const char *path, gt4gpu_header *out, uint64_t *num_locations)
+{
+  IndexHeader ih;
+  if (size < sizeof (ih)) return fail (GT4GPU_ERR_FORMAT, "%s: file too small for an index header", path);
+  memcpy (&ih, file, sizeof (ih));
+  if (ih.code != INDEX_CODE) return fail (GT4GPU_ERR_FORMAT, "%s: invalid file tag (%x, should be %x)", path, ih.code, INDEX_CODE);
+  if (ih.version_major != GT4GPU_VERSION_MAJOR)
+    return fail (GT4GPU_ERR_FORMAT, "%s: incompatible major version %u (required %u)", path, ih.version_major, GT4GPU_VERSION_MAJOR);
+  if (ih.kmers_start > size || (size - ih.kmers_start) / 16 < ih.num_words) return fail (GT4GPU_ERR_FORMAT, "%s: k-mer table exceeds the file", path);
+  memset (out, 0, sizeof (*out));
+  out->code = ih.code;
+  out->version_major = ih.version_major;
+  out->version_minor = ih.version_minor;
+  out->word_length = ih.word_length;
+  out->n_words = ih.num_words;
+  out->total_count = ih.num_locations;
+  out->list_start = ih.kmers_start;
+  out->word_bytes = 8;
+  out->count_bytes = 8;
+  if (num_locations) *num_locations = ih.num_locations;
+  return 0;
+}
+
+bool is_index_file (const unsigned char *file, uint64_t size)
+{
+  uint32_t code = 0;
+  if (size >= 4) memcpy (&code, file, 4);
+  return code == INDEX_CODE;
+}
+
+// index records [first, first + n) of a mapped GT4I file -> device SoA, chunked; every chunk carries one extra record
+// (the next word's offset) except the last one of the file, which is closed by num_locations
+int upload_index (const unsigned char *kmers, uint64_t n_total, uint64_t num_locations, uint64_t first, uint64_t n, uint64_t *d_words, uint32_t *d_counts)
+{
+  if (n == 0) return 0;
+  const uint64_t chunk = std::min<uint64_t> (n, 16ull << 20);
+  void *stage = nullptr;
+  int rc = dev_alloc (&stage, (chunk + 1) * 16);
+  if (rc) return rc;
+  cudaError_t e = cudaSuccess;
+  for (uint64_t done = 0; done < n && e == cudaSuccess; done += chunk) {
+    const uint64_t m = std::min (chunk, n - done);
+    const int has_next = (first + done + m < n_total) ? 1 : 0;
+    e = cudaMemcpyAsync (stage, kmers + (first + done) * 16, (m + has_next) * 16, cudaMemcpyHostToDevice, g_ctx.stream);
+    if (e == cudaSuccess) e = launch_index16 (stage, m, has_next, num_locations, d_words + done, d_counts + done, g_ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.stream);     // one staging buffer, pageable source
+  }
+  dev_free (stage);
+  if (e != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "index upload: %s", cudaGetErrorString (e));
   return 0;
 }
 
@@ -671,6 +734,7 @@ int gt4gpu_list_read_header (const char *path, int stream_mode, gt4gpu_header *o
   Mapping m;
   int rc = map_file (path, m);
   if (rc) return rc;
+  if (is_index_file (m.data, m.size)) return parse_index_header (m.data, m.size, path, out, nullptr);
   return parse_header (m.data, m.size, stream_mode, path, out);
 }
 
@@ -681,7 +745,9 @@ int gt4gpu_list_open_range (const char *path, int stream_mode, uint64_t first, u
   int rc = map_file (path, m);
   if (rc) return rc;
   gt4gpu_header h;
-  rc = parse_header (m.data, m.size, stream_mode, path, &h);
+  const bool index = is_index_file (m.data, m.size);     // glistcompare sniffs the 4-byte tag the same way (src/glistcompare.c:256-274)
+  uint64_t num_locations = 0;
+  rc = index ? parse_index_header (m.data, m.size, path, &h, &num_locations) : parse_header (m.data, m.size, stream_mode, path, &h);
   if (rc) return rc;
   if (first > h.n_words) first = h.n_words;
   if (count > h.n_words - first) count = h.n_words - first;
@@ -691,7 +757,8 @@ int gt4gpu_list_open_range (const char *path, int stream_mode, uint64_t first, u
   rc = new_list (count, h.word_length, &l);
   if (rc) return rc;
   l->sum_counts = h.total_count;
-  rc = upload_aos (m.data + h.list_start + first * 12, count, l->words, l->counts);
+  if (index) rc = upload_index (m.data + h.list_start, h.n_words, num_locations, first, count, l->words, l->counts);
+  else rc = upload_aos (m.data + h.list_start + first * 12, count, l->words, l->counts);
   if (rc) { gt4gpu_list_close (l); return rc; }
   *out = l;
   return 0;

@@ -5,8 +5,8 @@
  * Flag grammar, validation order, messages, output file names, tmp+rename behaviour, stdout text
  * and exit codes follow main() of /root/reference/src/glistcompare.c:84-429 (help text :1171-1196),
  * so that scripts such as MakeUnion.pl can switch binaries.  Not carried over (SURVEY.md section 2,
- * out of scope): -mm N with N > 0, -ss/--subset and GT4I index inputs; they exit with status 1 and a
- * message.  --stream selects the stream reader's header rules; --disable_scouts is accepted (there is
+ * out of scope): -mm N with N > 0 and -ss/--subset; they exit with status 1 and a message.  GT4I index files are
+ * accepted as inputs like the reference does (their k-mer table read as a list, counts = number of locations).  --stream selects the stream reader's header rules; --disable_scouts is accepted (there is
  * no read-ahead thread to disable).
  */
 #include <errno.h>
@@ -227,17 +227,13 @@ main (int argc, const char *argv[])
     }
     if (fread (tag, 1, 4, ifs) != 4) memset (tag, 0, 4);
     fclose (ifs);
-    if (!memcmp (tag, "C4TG", 4)) {
+    if (!memcmp (tag, "C4TG", 4) || !memcmp (tag, "I4TG", 4)) {     /* list, or index read as a list (:264-270) */
       if (gt4gpu_list_read_header (fnames[i], stream, &hdr)) {
         fprintf (stderr, "%s\n", gt4gpu_last_error ());
         fprintf (stderr, "Error: File %s is invalid or corrupted\n", fnames[i]);
         err = 1;
         continue;
       }
-    } else if (!memcmp (tag, "I4TG", 4)) {
-      fprintf (stderr, "Error: File %s is a GT4I index; index inputs are not supported by the GPU engine\n", fnames[i]);
-      err = 1;
-      continue;
     } else {
       fprintf (stderr, "Error: File %s has unknown format\n", fnames[i]);
       err = 1;

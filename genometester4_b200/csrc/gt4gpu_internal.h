@@ -62,6 +62,9 @@ cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items
 cudaError_t launch_deinterleave (const void *records, uint64_t n, uint64_t *words, uint32_t *counts, cudaStream_t st);
 cudaError_t launch_interleave (const uint64_t *words, const uint32_t *counts, uint64_t n, void *records, cudaStream_t st);
 
+// GT4I index records (16 bytes: word, first-location offset) -> SoA words / counts (offset differences)
+cudaError_t launch_index16 (const void *records, uint64_t n, int has_next, uint64_t end_loc, uint64_t *words, uint32_t *counts, cudaStream_t st);
+
 // counts[row(words_j[i]) * n_lists + j] = counts_j[i], rows found by binary search in `rows`
 cudaError_t launch_scatter_counts (const uint64_t *rows, uint64_t n_rows, const uint64_t *words, const uint32_t *counts,
                                    uint64_t n, unsigned j, unsigned n_lists, uint32_t *matrix, cudaStream_t st);

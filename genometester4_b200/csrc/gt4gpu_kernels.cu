@@ -328,6 +328,21 @@ interleave_kernel (const uint64_t *__restrict__ words, const uint32_t *__restric
   for (int x = threadIdx.x; x < m * 3; x += AOS_NT) dst[x] = s[x];
 }
 
+// GT4I index records (/root/reference/src/index-map.c:122-139): 16 bytes = u64 word + u64 offset of the word's first
+// location; the count of a word is the distance to the next word's offset (num_locations closes the last one).
+// rec holds n records, followed by one more record when has_next (its offset closes record n - 1), else end_loc does.
+__global__ void __launch_bounds__ (256)
+index16_kernel (const uint64_t *__restrict__ rec, uint64_t n, int has_next, uint64_t end_loc,
+                uint64_t *__restrict__ words, uint32_t *__restrict__ counts)
+{
+  const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t loc = rec[2 * i + 1];
+  const uint64_t next = (i + 1 < n || has_next) ? rec[2 * i + 3] : end_loc;
+  words[i] = rec[2 * i];
+  counts[i] = (uint32_t) (next - loc);
+}
+
 // counts of list j scattered into the row-major matrix; every word of the list is a row key
 __global__ void __launch_bounds__ (256)
 scatter_counts_kernel (const uint64_t *__restrict__ rows, uint64_t n_rows, const uint64_t *__restrict__ words,
@@ -415,6 +430,14 @@ cudaError_t launch_interleave (const uint64_t *words, const uint32_t *counts, ui
   if (n == 0) return cudaSuccess;
   const uint64_t grid = (n + AOS_PER_CTA - 1) / AOS_PER_CTA;
   interleave_kernel<<<(unsigned) grid, AOS_NT, 0, st>>> (words, counts, n, static_cast<uint32_t *> (records));
+  return cudaGetLastError ();
+}
+
+cudaError_t launch_index16 (const void *records, uint64_t n, int has_next, uint64_t end_loc, uint64_t *words, uint32_t *counts, cudaStream_t st)
+{
+  if (n == 0) return cudaSuccess;
+  const uint64_t grid = (n + 255) / 256;
+  index16_kernel<<<(unsigned) grid, 256, 0, st>>> (static_cast<const uint64_t *> (records), n, has_next, end_loc, words, counts);
   return cudaGetLastError ();
 }
 

@@ -37,11 +37,16 @@ def read_header(path, stream: bool = False) -> _lib.Header:
     return h
 
 
+INDEX_RECORD = np.dtype([("word", "<u8"), ("loc", "<u8")])      # GT4I k-mer table, /root/reference/src/index-map.c:122-139
+
+
 def map_records(path, header) -> np.ndarray:
-    """The file's records as a (read-only) numpy view with a 12-byte stride."""
+    """The file's records as a (read-only) numpy view: 12-byte list records, or 16-byte GT4I index records
+    (gt4gpu_list_read_header marks those with count_bytes == 8).  Only the keys are used (splitter planning)."""
+    dtype = INDEX_RECORD if header.count_bytes == 8 else api.RECORD
     if header.n_words == 0:
-        return np.zeros(0, dtype=api.RECORD)
-    return np.memmap(path, dtype=api.RECORD, mode="r", offset=header.list_start, shape=(header.n_words,))
+        return np.zeros(0, dtype=dtype)
+    return np.memmap(path, dtype=dtype, mode="r", offset=header.list_start, shape=(header.n_words,))
 
 
 def plan(paths, n_parts: int, stream: bool = False):

@@ -70,3 +70,10 @@ def test_synthetic_generators_numpy_and_torch_agree(k, m):
         w, c = synth.list_numpy(5, k, m, 0, m, j, 0.4)
         tw, tc = synth.list_torch(5, k, m, 0, m, j, 0.4, device="cpu", chunk=999)
         assert np.array_equal(w, tw.numpy().view(np.uint64)) and np.array_equal(c, tc.numpy().view(np.uint32))
+
+
+def test_index_header_is_readable_without_a_device():
+    h = _lib.Header()
+    idx = ROOT / "tests" / "golden" / "index" / "x_16.index"
+    assert _lib.load().gt4gpu_list_read_header(str(idx).encode(), 0, C.byref(h)) == 0
+    assert bytes(h)[:4] == b"I4TG" and (h.word_length, h.word_bytes, h.count_bytes) == (16, 8, 8) and h.n_words > 2000

@@ -85,3 +85,36 @@ def test_cli_vs_reference_binary_options(inputs, oracle):
             r = run_cli(args, run) if who == "mine" else oracle.run_ref("glistcompare", args, cwd=run)
             outs.append((r.returncode, r.stdout, {str(f.relative_to(run)): f.read_bytes() for f in sorted(run.rglob("*.list"))}))
         assert outs[0] == outs[1], args
+
+
+def test_gt4i_index_inputs_against_golden(tmp_path):
+    """GT4I index files as inputs (the reference reads their k-mer table through the same iterator interface,
+    /root/reference/src/index-map.c:122-158): library loader vs a numpy parse, CLI vs the reference's outputs."""
+    import numpy as np
+    import genometester4_b200 as g
+    idx_dir = Path(__file__).parent / "golden" / "index"
+    golden = json.loads((Path(__file__).parent / "golden" / "index_golden.json").read_text())
+    raw = (idx_dir / "x_16.index").read_bytes()
+    hdr = np.frombuffer(raw, dtype=[("code", "<u4"), ("major", "<u4"), ("minor", "<u4"), ("k", "<u4"), ("n", "<u8"), ("nloc", "<u8"),
+                                    ("fb", "<u4"), ("sb", "<u4"), ("pb", "<u4"), ("fill", "<u4"), ("files", "<u8"), ("kmers", "<u8"), ("locs", "<u8")], count=1)[0]
+    rec = np.frombuffer(raw, dtype=[("word", "<u8"), ("loc", "<u8")], count=int(hdr["n"]), offset=int(hdr["kmers"]))
+    counts = np.diff(np.concatenate([rec["loc"], [hdr["nloc"]]]).astype(np.uint64)).astype(np.uint32)
+    g.init(0)
+    l = g.WordList.open(idx_dir / "x_16.index")
+    assert (l.num_words, l.word_length, l.sum_counts) == (int(hdr["n"]), 16, int(hdr["nloc"]))
+    w, c = g.compare_wordmaps(l, g.WordList.from_arrays([], [], 16), find_union=1, cutoff=0)["union"].to_host()
+    assert np.array_equal(w, rec["word"]) and np.array_equal(c, counts)
+    part = g.WordList.open(idx_dir / "x_16.index", first=100, count=250)      # a shard that ends inside the table
+    w, c = g.compare_wordmaps(part, g.WordList.from_arrays([], [], 16), find_union=1, cutoff=0)["union"].to_host()
+    assert np.array_equal(w, rec["word"][100:350]) and np.array_equal(c, counts[100:350])
+    for case in golden:
+        for f in tmp_path.glob("out_*"):
+            f.unlink()
+        r = run_cli([idx_dir / f for f in case["files"]] + case["flags"], tmp_path)
+        assert r.returncode == case["rc"], r.stderr
+        got = {f.name: refrun.digest(f.read_bytes()) for f in sorted(tmp_path.glob("out_*"))}
+        assert got == case["outputs"], case
+        for f in tmp_path.glob("out_*"):
+            f.unlink()
+        r = run_cli([idx_dir / f for f in case["files"]] + case["flags"] + ["--count_only"], tmp_path)
+        assert r.stdout.decode() == case["count_only_stdout"], case
