@@ -248,6 +248,31 @@ def workload_config(args, na, nb, sample=False):
 
 # ------------------------------------------------------------------------------------------ our arm
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Best effort: run this rank (and allocate its pinned host buffers) on the NUMA node its GPU hangs off, so that the
+    end-to-end path does not cross sockets.  Returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_gt4gpu_arm(args):
     import numpy as np
     import torch
@@ -262,6 +287,7 @@ def run_gt4gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; genometester4_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     g.init(local)
@@ -367,7 +393,7 @@ def run_gt4gpu_arm(args):
                 "dtype": "u64 keys / u32 counts (integer compare, add mod 2^32)", "data": "synthetic",
                 "config": workload_config(args, na, nb), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks,
-                "output_kmers": total_out, "input_kmers": total_in, "kernel_config": {"kernel": kernel_name, "stream_shape": args.stream_shape or os.environ.get("GT4GPU_STREAM_SHAPE", "512x9"),
+                "output_kmers": total_out, "input_kmers": total_in, "numa_node_rank0": numa_node, "kernel_config": {"kernel": kernel_name, "stream_shape": args.stream_shape or os.environ.get("GT4GPU_STREAM_SHAPE", "512x9"),
                                   "tile": args.tile or os.environ.get("GT4GPU_TILE", "256x9")}}
         print(json.dumps(line), flush=True)
     if world > 1:
