@@ -158,6 +158,10 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   unsigned char *ws = nullptr;
   int rc = dev_alloc ((void **) &ws, hdr_bytes + desc_bytes + part_bytes);
   if (rc) return rc;
+  struct ScratchGuard {      // the scratch goes back to the pool on every exit path
+    unsigned char *&p;
+    ~ScratchGuard () { if (p) { dev_free (p); p = nullptr; } }
+  } guard{ws};
   CU (cudaMemsetAsync (ws, 0, hdr_bytes + desc_bytes, st));
 
   TileArgs args;
@@ -207,7 +211,6 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   CallHeader h;
   CU (cudaMemcpyAsync (&h, ws, sizeof (h), cudaMemcpyDeviceToHost, st));
   CU (cudaStreamSynchronize (st));
-  dev_free (ws);
   float ms = 0.f;
   CU (cudaEventElapsedTime (&ms, tl_ev[0], tl_ev[1]));
   tl_ms_partition += ms;
