@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -56,6 +57,7 @@ struct Context {
   int sm_count = 0;
 };
 Context g_ctx;
+std::mutex g_init_mutex;      // gt4gpu_init / gt4gpu_shutdown; the merge entry points only read the context
 
 thread_local char tl_error[512] = "";
 thread_local float tl_ms_partition = 0.f, tl_ms_merge = 0.f;
@@ -630,6 +632,7 @@ void gt4gpu_header_init (gt4gpu_header *hdr, uint32_t word_length)
 
 int gt4gpu_init (int device)
 {
+  std::lock_guard<std::mutex> lock (g_init_mutex);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount (&count);
   if (e != cudaSuccess || count == 0)
@@ -669,6 +672,7 @@ int gt4gpu_init (int device)
 
 void gt4gpu_shutdown (void)
 {
+  std::lock_guard<std::mutex> lock (g_init_mutex);
   if (!g_ctx.ready) return;
   cudaStreamSynchronize (g_ctx.stream);
   if (g_ctx.own_stream) cudaStreamDestroy (g_ctx.own_stream);
