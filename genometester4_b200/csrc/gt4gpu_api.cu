@@ -236,6 +236,7 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
     if (v[5]) fprintf (stderr, "gt4gpu debug: consumer warp cycles per tile: wait %.0f search %.0f merge %.0f scan+barrier %.0f scatter %.0f (warp-tiles %llu)\n",
                        (double) v[0] / v[5], (double) v[1] / v[5], (double) v[2] / v[5], (double) v[3] / v[5], (double) v[4] / v[5], v[5]);
   }
+  if (h.overflow == 2u) return fail (GT4GPU_ERR_ARG, "input lists are not strictly ascending (the merge result is undefined)");
   if (h.overflow) return fail (GT4GPU_ERR_CAPACITY, "output buffer too small for the merge result");
   for (int s = 0; s < 4; s++) {
     if (!((stream_mask >> s) & 1u)) continue;

@@ -127,8 +127,14 @@ setop2_tile_kernel (const TileArgs args)
   const uint64_t total = args.na + args.nb;
   const uint64_t d_lo = tile * TILE;
   const uint64_t d_hi = (d_lo + TILE < total) ? d_lo + TILE : total;
-  const uint64_t a_lo = args.part[tile], a_hi = args.part[tile + 1];
-  const uint64_t b_lo = d_lo - a_lo, b_hi = d_hi - a_hi;
+  const uint64_t a_lo = args.part[tile];
+  uint64_t a_hi = args.part[tile + 1];
+  const bool sane = a_hi >= a_lo && a_hi - a_lo <= d_hi - d_lo;     // false only for inputs that are not strictly ascending
+  if (!sane) {
+    if (threadIdx.x == 0) args.hdr->overflow = 2u;
+    a_hi = a_lo;
+  }
+  const uint64_t b_lo = d_lo - a_lo, b_hi = sane ? d_hi - a_hi : b_lo;
   const int na = (int) (a_hi - a_lo), nb = (int) (b_hi - b_lo);
   const bool has_halo = a_lo > 0;
   const bool has_peek = b_hi < args.nb;

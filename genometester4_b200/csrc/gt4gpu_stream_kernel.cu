@@ -317,7 +317,7 @@ setop2_stream_kernel (const TileArgs args)
         pf_tile = nxt + pf_dist;
         if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
       }
-      if (!COUNT_ONLY && (args.debug & 4) == 0 && cur_pf < n_tiles) {   // (the count-only pass is faster without it)
+      if (!COUNT_ONLY && (args.debug & 4) == 0 && cur_pf < n_tiles && cur_pf_hi >= cur_pf_lo && cur_pf_hi - cur_pf_lo <= (uint64_t) TILE) {   // (the count-only pass is faster without it)
         const uint64_t pd_lo = cur_pf * TILE;
         const uint64_t pd_hi = (pd_lo + TILE < total) ? pd_lo + TILE : total;
         const uint64_t pb_lo = pd_lo - cur_pf_lo, pb_hi = pd_hi - cur_pf_hi;
@@ -341,8 +341,13 @@ setop2_stream_kernel (const TileArgs args)
       }
       const uint64_t d_lo = tile * TILE;
       const uint64_t d_hi = (d_lo + TILE < total) ? d_lo + TILE : total;
-      const uint64_t b_lo = d_lo - a_lo, b_hi = d_hi - a_hi;
-      const int na = (int) (a_hi - a_lo), nb = (int) (b_hi - b_lo);
+      // co-ranks of strictly ascending lists are monotone with 0 <= a_hi - a_lo <= d_hi - d_lo; anything else means the
+      // inputs are not sorted: stage an empty tile and report it instead of copying out of bounds
+      const bool sane = a_hi >= a_lo && a_hi - a_lo <= d_hi - d_lo;
+      if (!sane) args.hdr->overflow = 2u;
+      const uint64_t a_hi_ok = sane ? a_hi : a_lo;
+      const uint64_t b_lo = d_lo - a_lo, b_hi = sane ? d_hi - a_hi : b_lo;
+      const int na = (int) (a_hi_ok - a_lo), nb = (int) (b_hi - b_lo);
       const int halo = a_lo > 0 ? 1 : 0, peek = b_hi < args.nb ? 1 : 0;
       uint64_t *sk = stage_keys (s);
       uint32_t *sc = stage_cnts (s);
@@ -350,9 +355,9 @@ setop2_stream_kernel (const TileArgs args)
       // Byte ranges to stage.  A block is laid out from the 16-byte boundary below its first byte to the one above
       // its last byte (TMA bulk copies need 16-byte aligned addresses and sizes).  Nothing outside the arrays is
       // ever read: see the edge case below.
-      const uintptr_t ak0 = (uintptr_t) (args.a_words + a_lo - halo), ak1 = (uintptr_t) (args.a_words + a_hi);
+      const uintptr_t ak0 = (uintptr_t) (args.a_words + a_lo - halo), ak1 = (uintptr_t) (args.a_words + a_hi_ok);
       const uintptr_t bk0 = (uintptr_t) (args.b_words + b_lo), bk1 = (uintptr_t) (args.b_words + b_hi + peek);
-      const uintptr_t ac0 = (uintptr_t) (args.a_counts + a_lo - halo), ac1 = (uintptr_t) (args.a_counts + a_hi);
+      const uintptr_t ac0 = (uintptr_t) (args.a_counts + a_lo - halo), ac1 = (uintptr_t) (args.a_counts + a_hi_ok);
       const uintptr_t bc0 = (uintptr_t) (args.b_counts + b_lo), bc1 = (uintptr_t) (args.b_counts + b_hi + peek);
       const uintptr_t ak0a = ak0 & ~(uintptr_t) 15, bk0a = bk0 & ~(uintptr_t) 15, ac0a = ac0 & ~(uintptr_t) 15, bc0a = bc0 & ~(uintptr_t) 15;
       const uint32_t ak_bytes = (ak1 > ak0) ? (uint32_t) (((ak1 + 15) & ~(uintptr_t) 15) - ak0a) : 0u;

@@ -394,3 +394,33 @@ def test_sharded_driver_single_rank_gpu(g, oracle, tmp_path):
         lb = g.WordList.open(tmp_path / "B.list", first=int(bounds[1, r]), count=int(bounds[1, r + 1] - bounds[1, r]))
         parts.append(g.compare_wordmaps(la, lb, find_union=1, cutoff=2)["union"].records())
     assert np.concatenate(parts).tobytes() == want["union"].records().tobytes()
+
+
+def test_unsorted_inputs_never_crash_the_device(g, oracle):
+    """The reference produces garbage for lists that are not strictly ascending; so may we, but never an out-of-bounds
+    access: either a (meaningless) result or error 1 comes back, and the context stays usable."""
+    rng = np.random.default_rng(123)
+    for trial in range(6):
+        n = [50_000, 200_001, 7, 4609, 123_457, 99_999][trial]
+        bad = rng.integers(0, 1 << 50, size=n, dtype=np.uint64)                      # unsorted, with duplicates
+        if trial % 2:
+            bad = np.sort(bad)[::-1].copy()                                             # strictly descending
+        good = np.unique(rng.integers(0, 1 << 50, size=n, dtype=np.uint64))
+        cnt = np.ones(n, np.uint32)
+        lb_, lg_ = g.WordList.from_arrays(bad, cnt, 25), g.WordList.from_arrays(good, cnt[:good.size], 25)
+        for a_, b_ in ((lb_, lg_), (lg_, lb_), (lb_, lb_)):
+            for kw in (dict(find_union=1), dict(find_intrsec=1, countonly=1), dict(find_union=1, find_diff=1)):
+                for use_stream in (1, 0):
+                    g.set_option("use_stream_kernel", use_stream)
+                    try:
+                        r = g.compare_wordmaps(a_, b_, **kw)
+                        for v in r.values():
+                            assert v.n_words <= len(a_) + len(b_)
+                    except g.GT4GPUError as e:
+                        assert e.code in (1, 5), e      # "not ascending" or "more output than any valid input could give"
+        g.set_option("use_stream_kernel", 1)
+    # the device is still healthy
+    a, b = make_pair(5, 30_000, 20_000, 10_000, 25, "tail")
+    want = oracle.compare2(oracle.SList(*a, 25), oracle.SList(*b, 25), union=True)["union"]
+    w, c = g.compare_wordmaps(g.WordList.from_arrays(*a, 25), g.WordList.from_arrays(*b, 25), find_union=1)["union"].to_host()
+    assert np.array_equal(w, want.words) and np.array_equal(c, want.counts)
