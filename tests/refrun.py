@@ -94,3 +94,23 @@ def run_reference(tmp: Path, paths, ops, rule, cutoff, count_only=False, extra=(
 
 def digest(b: bytes) -> str:
     return hashlib.sha256(b).hexdigest()
+
+
+def build_config1_lists(tmp: Path):
+    """BASELINE config 1: a 1.1 Mbp uniform random genome (python random, seed 11) and a copy
+    with 1 % point substitutions, turned into k = 16 lists by the UNMODIFIED reference glistmaker.  Returns the two
+    list paths, or None when oracle/_ref is not available."""
+    import random
+    if O.ref_binary("glistmaker") is None:
+        return None
+    tmp.mkdir(parents=True, exist_ok=True)
+    rnd = random.Random(11)
+    g1 = "".join(rnd.choice("ACGT") for _ in range(1_100_000))
+    r2 = random.Random(12)
+    g2 = "".join(r2.choice("ACGT") if r2.random() < 0.01 else c for c in g1)
+    out = []
+    for name, s in (("g1", g1), ("g2", g2)):
+        (tmp / f"{name}.fa").write_text(f">{name}\n" + "\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n")
+        O.run_ref("glistmaker", [f"{name}.fa", "-w", "16", "-o", name], cwd=tmp, check=True)
+        out.append(tmp / f"{name}_16.list")
+    return out

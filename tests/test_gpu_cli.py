@@ -118,3 +118,20 @@ def test_gt4i_index_inputs_against_golden(tmp_path):
             f.unlink()
         r = run_cli([idx_dir / f for f in case["files"]] + case["flags"] + ["--count_only"], tmp_path)
         assert r.stdout.decode() == case["count_only_stdout"], case
+
+
+def test_config1_fasta_built_lists(tmp_path, oracle):
+    """BASELINE config 1 on the GPU: the two ~1.1 M-k-mer k=16 lists built by the reference glistmaker from synthetic
+    FASTA, `-i` (and `-u -d`) through the CLI, byte-identical to the reference glistcompare."""
+    paths = refrun.build_config1_lists(tmp_path / "c1")
+    if paths is None:
+        pytest.skip("oracle/_ref not built")
+    for flags in (["-i"], ["-u", "-d", "-c", "2"]):
+        outs = []
+        for who in ("mine", "ref"):
+            run = tmp_path / f"{who}_{len(flags)}"
+            run.mkdir()
+            r = run_cli([*paths, *flags], run) if who == "mine" else oracle.run_ref("glistcompare", [*paths, *flags], cwd=run)
+            assert r.returncode == 0
+            outs.append({f.name: f.read_bytes() for f in sorted(run.glob("out_*"))})
+        assert outs[0] == outs[1] and len(outs[0]) == len([f for f in flags if f in ("-i", "-u", "-d")])

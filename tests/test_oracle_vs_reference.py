@@ -86,3 +86,17 @@ def test_oracle_vs_reference_binary_multi_full(oracle, tmp_path):
         assert ref_stdout == stdout, (name, ops, rule, cutoff)
         n += 1
     assert n > 300
+
+
+def test_config1_glistmaker_lists_intersection(oracle, tmp_path):
+    """BASELINE config 1 end to end on the CPU: glistmaker-built k=16 lists, `glistcompare -i`."""
+    paths = refrun.build_config1_lists(tmp_path / "c1")
+    if paths is None:
+        pytest.skip("oracle/_ref not built")
+    a, b = oracle.read_list(paths[0]), oracle.read_list(paths[1])
+    assert len(a) > 1_000_000 and len(b) > 1_000_000 and a.word_length == 16
+    rc, ref_files, _ = refrun.run_reference(tmp_path / "run", paths, ("-i",), "default", 1)
+    want = oracle.compare2(a, b, intrsec=True)["intrsec"]
+    assert rc == 0 and ref_files == {"out_16_intrsec.list": refrun.list_bytes(want, 16)}
+    rc, _, stdout = refrun.run_reference(tmp_path / "run", paths, ("-i",), "default", 1, count_only=True)
+    assert stdout == f"NUnique\t{want.n_words}\nNTotal\t{want.total_count}\n"
