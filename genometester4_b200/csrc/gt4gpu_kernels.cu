@@ -90,6 +90,35 @@ partition_kernel (const uint64_t *__restrict__ a, uint64_t na, const uint64_t *_
   part[t] = merge_path<uint64_t> (a, na, b, nb, diag);
 }
 
+// Two-level variant for long lists.  A full-range search touches ~log2(n) scattered cache lines
+// (and TLB entries) per boundary; searching every PART_COARSE-th boundary first and the rest inside
+// the window its two coarse neighbours span keeps all but ~1.5% of the searches inside a few MB.
+static constexpr uint64_t PART_COARSE = 64;
+
+__global__ void __launch_bounds__ (256)
+partition_coarse_kernel (const uint64_t *__restrict__ a, uint64_t na, const uint64_t *__restrict__ b, uint64_t nb,
+                         uint32_t tile, uint64_t n_tiles, uint64_t *__restrict__ part)
+{
+  uint64_t t = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) * PART_COARSE;
+  if (t >= n_tiles + PART_COARSE) return;
+  if (t > n_tiles) t = n_tiles;
+  const uint64_t total = na + nb;
+  uint64_t diag = t * tile;
+  if (diag > total) diag = total;
+  part[t] = merge_path<uint64_t> (a, na, b, nb, diag);
+}
+
+__global__ void __launch_bounds__ (256)
+partition_fine_kernel (const uint64_t *__restrict__ a, uint64_t na, const uint64_t *__restrict__ b, uint64_t nb,
+                       uint32_t tile, uint64_t n_tiles, uint64_t *__restrict__ part)
+{
+  const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles || (t % PART_COARSE) == 0) return;     // coarse boundaries (and the last one) are done
+  const uint64_t t0 = t - t % PART_COARSE;
+  const uint64_t t1 = t0 + PART_COARSE < n_tiles ? t0 + PART_COARSE : n_tiles;
+  part[t] = merge_path_window<uint64_t> (a, na, b, nb, t * tile, part[t0], part[t1]);
+}
+
 // ------------------------------------------------------------------------------------------
 // the tile kernel
 // ------------------------------------------------------------------------------------------
@@ -389,7 +418,13 @@ cudaError_t launch_partition (const uint64_t *a, uint64_t na, const uint64_t *b,
 {
   const uint64_t n = n_tiles + 1;
   const unsigned grid = (unsigned) ((n + 255) / 256);
-  partition_kernel<<<grid, 256, 0, st>>> (a, na, b, nb, tile, n_tiles, part);
+  if (n_tiles < 16 * PART_COARSE) {
+    partition_kernel<<<grid, 256, 0, st>>> (a, na, b, nb, tile, n_tiles, part);
+    return cudaGetLastError ();
+  }
+  const uint64_t n_coarse = n_tiles / PART_COARSE + 2;
+  partition_coarse_kernel<<<(unsigned) ((n_coarse + 255) / 256), 256, 0, st>>> (a, na, b, nb, tile, n_tiles, part);
+  partition_fine_kernel<<<grid, 256, 0, st>>> (a, na, b, nb, tile, n_tiles, part);
   return cudaGetLastError ();
 }
 
