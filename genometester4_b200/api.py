@@ -272,6 +272,28 @@ def gt4_write_union(arrays, cutoff: int, ofile: int = 0) -> Header:
     return h
 
 
+def sequence_words(text: bytes, word_length: int) -> np.ndarray:
+    """Canonical words of a FastA/FastQ image in file order (fasta_reader_read_nwords, src/fasta.c:88-290).  Host only.
+    Raises GT4GPUError(code 3) where the reference's reader reports a format error."""
+    n = C.c_uint64()
+    out = np.empty(max(1, len(text)), dtype=np.uint64)
+    _check(_lib.load().gt4gpu_sequence_words(text, len(text), word_length, C.c_void_p(out.ctypes.data), out.size, C.byref(n)))
+    return out[:n.value].copy()
+
+
+def count_words(words, word_length: int, n_words: int | None = None) -> Result:
+    """Back end of glistmaker for one table of raw words: sort (wordtable_sort, src/word-table.c) and count the
+    occurrences of every distinct word (merge_tables_to_file, src/glistmaker.c:1080-1144).  ``words`` is a numpy
+    uint64 array (host) or an int device pointer with ``n_words``; returns the sorted (word, count) list."""
+    out = CResult()
+    if isinstance(words, int):
+        _check(_lib.load().gt4gpu_count_words(C.c_void_p(words), n_words, 1, word_length, C.byref(out)))
+    else:
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        _check(_lib.load().gt4gpu_count_words(C.c_void_p(w.ctypes.data), w.size, 0, word_length, C.byref(out)))
+    return _wrap(out)
+
+
 def _matrix(lists, is_union: bool):
     lib = _lib.load()
     n = C.c_uint64()

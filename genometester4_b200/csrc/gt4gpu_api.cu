@@ -1071,6 +1071,175 @@ int gt4gpu_union_matrix (const gt4gpu_list *const *lists, unsigned n_lists, int 
 
 // ------------------------------------------------------------------ results
 
+// ------------------------------------------------------------------ list building
+
+// Host-side reader of FastA / FastQ images (fasta_reader_read_nwords, src/fasta.c:88-290, with canonize = 1 as
+// glistmaker sets it, src/listmaker-queue.c:196).  Table driven: every byte is a nucleotide (0..3), a word break
+// (printable, not ACGTU) or skipped (control characters such as line ends, :263-269).
+namespace {
+
+enum : uint8_t { CH_BREAK = 4, CH_SKIP = 5 };
+
+struct CharClass {
+  uint8_t v[256];
+  CharClass ()
+  {
+    for (int c = 0; c < 256; c++) v[c] = c < ' ' ? CH_SKIP : CH_BREAK;
+    v['A'] = v['a'] = 0;
+    v['C'] = v['c'] = 1;
+    v['G'] = v['g'] = 2;
+    v['T'] = v['t'] = v['U'] = v['u'] = 3;
+  }
+};
+const CharClass g_chars;
+
+struct WordWindow {       // the sliding forward / reverse-complement pair of one reader
+  uint64_t fw = 0, rc = 0, mask;
+  unsigned have = 0, k, top;
+  explicit WordWindow (unsigned k_) : mask (k_ >= 32 ? ~0ull : (1ull << (2 * k_)) - 1), k (k_), top (2 * (k_ - 1)) {}
+  void reset () { fw = rc = 0; have = 0; }
+  bool push (unsigned nucl, uint64_t *word)
+  {
+    fw = ((fw << 2) | nucl) & mask;
+    rc = (rc >> 2) | ((uint64_t) (3u - nucl) << top);
+    if (have < k) have++;
+    if (have < k) return false;
+    *word = fw < rc ? fw : rc;
+    return true;
+  }
+};
+
+}  // namespace
+
+int gt4gpu_sequence_words (const void *text, uint64_t n_bytes, uint32_t word_length, uint64_t *words, uint64_t capacity,
+                           uint64_t *n_words)
+{
+  if ((!text && n_bytes) || !n_words) return fail (GT4GPU_ERR_ARG, "null argument");
+  if (word_length < 1 || word_length > 32) return fail (GT4GPU_ERR_ARG, "word length %u not in 1..32", word_length);
+  const unsigned char *p = static_cast<const unsigned char *> (text), *const end = p + n_bytes;
+  *n_words = 0;
+  if (p == end || *p == 0) return 0;
+  const bool fastq = (*p == '@');
+  if (!fastq && *p != '>') return fail (GT4GPU_ERR_FORMAT, "invalid start tag '%c'", *p);    // :136-139
+  WordWindow win (word_length);
+  uint64_t n = 0;
+  auto emit_run = [&] (const unsigned char *q, const unsigned char *stop, unsigned char terminator) -> const unsigned char * {
+    // nucleotides up to `terminator` (or a zero byte / the end of the image)
+    for (; q < stop && *q != terminator && *q != 0; q++) {
+      const uint8_t cls = g_chars.v[*q];
+      if (cls < CH_BREAK) {
+        uint64_t w;
+        if (win.push (cls, &w)) {
+          if (words) {
+            if (n >= capacity) return nullptr;
+            words[n] = w;
+          }
+          n++;
+        }
+      } else if (cls == CH_BREAK) {
+        win.reset ();
+      }
+    }
+    return q;
+  };
+  int rc = 0;
+  while (p < end && *p != 0) {
+    // p is on a record tag ('>' or '@'): the name runs to the end of the line
+    const unsigned char *nl = static_cast<const unsigned char *> (memchr (p, '\n', (size_t) (end - p)));
+    const unsigned char *zero = static_cast<const unsigned char *> (memchr (p, 0, (size_t) ((nl ? nl : end) - p)));
+    if (zero || !nl) break;                    // the image ends inside a name
+    p = nl + 1;
+    win.reset ();
+    if (!fastq) {
+      p = emit_run (p, end, '>');              // a '>' anywhere in the sequence starts the next name (:177-190)
+      if (!p) { rc = GT4GPU_ERR_CAPACITY; break; }
+    } else {
+      p = emit_run (p, end, '\n');             // one line of sequence (:191)
+      if (!p) { rc = GT4GPU_ERR_CAPACITY; break; }
+      if (p >= end || *p == 0) break;          // the image ends inside the sequence
+      p++;
+      if (p >= end || *p != '+') { rc = GT4GPU_ERR_FORMAT; break; }     // :203-206
+      const unsigned char *q = static_cast<const unsigned char *> (memchr (p, '\n', (size_t) (end - p)));
+      if (!q || memchr (p, 0, (size_t) (q - p))) { rc = GT4GPU_ERR_FORMAT; break; }   // :210-214
+      p = q + 1;                               // quality line
+      q = static_cast<const unsigned char *> (memchr (p, '\n', (size_t) (end - p)));
+      if (!q || memchr (p, 0, (size_t) (q - p))) { p = end; break; }     // EOF inside the quality: nothing more to read
+      p = q + 1;
+      if (p >= end || *p == 0) break;
+      if (*p != '@') { rc = GT4GPU_ERR_FORMAT; break; }                 // :284-287
+    }
+  }
+  *n_words = n;
+  if (rc == GT4GPU_ERR_CAPACITY) return fail (rc, "word buffer too small");
+  if (rc) return fail (rc, "malformed FastQ record");
+  return 0;
+}
+
+int gt4gpu_count_words (const uint64_t *words, uint64_t n_words, int on_device, uint32_t word_length, gt4gpu_result *out)
+{
+  if (!out || (!words && n_words)) return fail (GT4GPU_ERR_ARG, "null argument");
+  if (word_length < 1 || word_length > 32) return fail (GT4GPU_ERR_ARG, "word length %u not in 1..32", word_length);
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  reset_timing ();
+  cudaStream_t st = g_ctx.stream;
+  memset (out, 0, sizeof (*out));
+  out->word_length = word_length;
+  if (n_words == 0) return 0;
+
+  // words are < 4^k: only the low 2k bits need sorting
+  const int n_pass = (int) ((2 * word_length + 7) / 8);
+  const uint64_t n = n_words;
+  struct Scratch {          // every temporary goes back to the pool on every exit path
+    void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Scratch () { for (void *q : p) dev_free (q); }
+  } tmp;
+  uint64_t *keys = nullptr, *alt = nullptr, *first = nullptr;
+  unsigned char *ws_sort = nullptr, *ws_rle = nullptr;
+  if ((rc = dev_alloc (&tmp.p[0], n * sizeof (uint64_t)))) return rc;
+  if ((rc = dev_alloc (&tmp.p[1], n * sizeof (uint64_t)))) return rc;
+  if ((rc = dev_alloc (&tmp.p[2], sort_scratch_bytes (n)))) return rc;
+  keys = (uint64_t *) tmp.p[0]; alt = (uint64_t *) tmp.p[1]; ws_sort = (unsigned char *) tmp.p[2];
+  CU (cudaMemcpyAsync (keys, words, n * sizeof (uint64_t), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+
+  for (int i = 0; i < 3; i++) if (!tl_ev[i]) CU (cudaEventCreate (&tl_ev[i]));
+  CU (cudaEventRecord (tl_ev[0], st));
+  uint64_t *sorted = nullptr;
+  CU (launch_radix_sort (keys, alt, n, n_pass, ws_sort, g_ctx.sm_count, &sorted, st));
+  CU (cudaEventRecord (tl_ev[1], st));
+  uint64_t *words_tmp = (sorted == keys) ? alt : keys;      // the buffer the sort no longer needs
+  if ((rc = dev_alloc (&tmp.p[3], n * sizeof (uint64_t)))) return rc;
+  if ((rc = dev_alloc (&tmp.p[4], rle_scratch_bytes (n)))) return rc;
+  first = (uint64_t *) tmp.p[3]; ws_rle = (unsigned char *) tmp.p[4];
+  unsigned long long *d_unique = nullptr;
+  CU (launch_rle_heads (sorted, n, words_tmp, first, ws_rle, &d_unique, st));
+  unsigned long long n_unique = 0;
+  CU (cudaMemcpyAsync (&n_unique, d_unique, sizeof (n_unique), cudaMemcpyDeviceToHost, st));
+  CU (cudaStreamSynchronize (st));
+  if (n_unique == 0 || n_unique > n) return fail (GT4GPU_ERR_CUDA, "run-length pass returned %llu runs for %llu words", n_unique, (unsigned long long) n);
+
+  uint64_t *res_words = nullptr;
+  uint32_t *res_counts = nullptr;
+  if ((rc = dev_alloc ((void **) &res_words, n_unique * sizeof (uint64_t)))) return rc;
+  if ((rc = dev_alloc ((void **) &res_counts, n_unique * sizeof (uint32_t)))) { dev_free (res_words); return rc; }
+  cudaError_t e = launch_rle_counts (words_tmp, first, n_unique, n, res_words, res_counts, st);
+  if (e == cudaSuccess) e = cudaEventRecord (tl_ev[2], st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize (st);
+  if (e != cudaSuccess) {
+    dev_free (res_words); dev_free (res_counts);
+    return fail (GT4GPU_ERR_CUDA, "run-length pass: %s", cudaGetErrorString (e));
+  }
+  cudaEventElapsedTime (&tl_ms_partition, tl_ev[0], tl_ev[1]);     // sort
+  cudaEventElapsedTime (&tl_ms_merge, tl_ev[1], tl_ev[2]);         // run-length encoding
+  tl_launches = 2 + n_pass + 2;
+  out->n_words = n_unique;
+  out->total_count = n;          // every word occurrence is counted once (merge_tables_to_file, :1139)
+  out->words = res_words;
+  out->counts = res_counts;
+  out->capacity = n_unique;
+  return 0;
+}
+
 int gt4gpu_result_to_host_soa (const gt4gpu_result *res, uint64_t *words, uint32_t *counts)
 {
   if (!res) return fail (GT4GPU_ERR_ARG, "null argument");

@@ -69,4 +69,16 @@ cudaError_t launch_index16 (const void *records, uint64_t n, int has_next, uint6
 cudaError_t launch_scatter_counts (const uint64_t *rows, uint64_t n_rows, const uint64_t *words, const uint32_t *counts,
                                    uint64_t n, unsigned j, unsigned n_lists, uint32_t *matrix, cudaStream_t st);
 
+// ---- list building (gt4gpu_sort_kernel.cu): least-significant-digit radix sort of raw words + run-length counts
+static constexpr int SORT_MAX_PASSES = 8;                                        // 8-bit digits of a 64-bit word
+static constexpr size_t SORT_SCRATCH_HEAD = 2 * SORT_MAX_PASSES * 256 * 8 + 256;  // histograms, bin starts, tickets
+size_t sort_scratch_bytes (uint64_t n);
+cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch, int sm_count,
+                               uint64_t **sorted, cudaStream_t st);
+size_t rle_scratch_bytes (uint64_t n);
+cudaError_t launch_rle_heads (const uint64_t *sorted, uint64_t n, uint64_t *words_tmp, uint64_t *first, unsigned char *scratch,
+                              unsigned long long **d_n_unique, cudaStream_t st);
+cudaError_t launch_rle_counts (const uint64_t *words_tmp, const uint64_t *first, uint64_t n_unique, uint64_t n,
+                               uint64_t *words, uint32_t *counts, cudaStream_t st);
+
 }  // namespace gt4gpu

@@ -177,6 +177,24 @@ int gt4gpu_write_union (const gt4gpu_list *const *lists, unsigned n_lists, uint3
 int gt4gpu_union_matrix (const gt4gpu_list *const *lists, unsigned n_lists, int is_union,
                          uint64_t *words, uint32_t *counts, uint64_t max_rows, uint64_t *n_rows);
 
+/* ---- list building (the step before the merge) ----------- */
+
+/* Replaces fasta_reader_read_nwords (src/fasta.c:88-290) as glistmaker drives it (read_table, src/glistmaker.c:922;
+ * canonize = 1, src/listmaker-queue.c:196): HOST-side parse of a FastA / FastQ image into the canonical word of every
+ * k-mer, in file order.  words may be NULL to only count (size the buffer with a first call, or use n_bytes as the
+ * bound).  GT4GPU_ERR_FORMAT where the reader gives up (bad start tag, FastQ '+' / '@' missing): *n_words then holds
+ * the words read so far, as glistmaker keeps them.  No device work. */
+int gt4gpu_sequence_words (const void *text, uint64_t n_bytes, uint32_t word_length, uint64_t *words, uint64_t capacity,
+                           uint64_t *n_words);
+/* Replaces the back end of glistmaker for one table of raw words: wordtable_sort (src/word-table.c, radix sort of
+ * src/utils.c:127-198, called from read_table, src/glistmaker.c:893-968) followed by the run-length counting of
+ * merge_tables_to_file (src/glistmaker.c:1080-1144).  words: n_words canonical k-mer words (< 4^word_length) in any
+ * order, duplicates included, in HOST (on_device = 0) or DEVICE memory; the input is not modified.  out: the distinct
+ * words ascending with their number of occurrences (device arrays, library-owned), total_count = n_words.  Several
+ * tables are collated with gt4gpu_union_multi / gt4gpu_write_union (rule add, cutoff 1) like collate_files (:787-835).
+ * gt4gpu_last_timing afterwards reports the sort as ms_partition and the run-length pass as ms_merge. */
+int gt4gpu_count_words (const uint64_t *words, uint64_t n_words, int on_device, uint32_t word_length, gt4gpu_result *out);
+
 /* ---- results -------------------------------------------------------------------------- */
 
 int gt4gpu_result_to_host_soa (const gt4gpu_result *res, uint64_t *words, uint32_t *counts);

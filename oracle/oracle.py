@@ -184,6 +184,30 @@ def union_matrix(lists, is_union=False):
     return 0, words[:n.value], counts[:n.value]
 
 
+def sequence_words(text: bytes, word_length: int) -> np.ndarray:
+    """Canonical words of a FastA/FastQ image in file order (fasta_reader_read_nwords, src/fasta.c:88-290)."""
+    n = C.c_uint64()
+    buf = (C.c_ubyte * max(1, len(text))).from_buffer_copy(text or b"\0")
+    out = np.empty(max(1, len(text)), dtype=np.uint64)
+    rc = lib().gt4o_sequence_words(buf, C.c_uint64(len(text)), C.c_uint(word_length), C.c_void_p(out.ctypes.data),
+                                   C.c_uint64(out.size), C.byref(n))
+    if rc:
+        raise ValueError(f"sequence reader error {rc}")
+    return out[:n.value].copy()
+
+
+def count_words(words, word_length: int) -> SList:
+    """Sorted (word, count) list of one table of raw words (wordtable_sort + merge_tables_to_file,
+    src/glistmaker.c:1080-1144)."""
+    w = np.array(words, dtype=np.uint64)
+    ow = np.empty(max(1, w.size), dtype=np.uint64)
+    oc = np.empty(max(1, w.size), dtype=np.uint32)
+    lib().gt4o_count_words.restype = C.c_uint64
+    u = lib().gt4o_count_words(C.c_void_p(w.ctypes.data), C.c_uint64(w.size), C.c_void_p(ow.ctypes.data),
+                               C.c_void_p(oc.ctypes.data))
+    return SList(ow[:u].copy(), oc[:u].copy(), word_length)
+
+
 def calculate_freq(f1, f2, rule, count_override=1):
     rule = RULES[rule] if isinstance(rule, str) else int(rule)
     return lib().gt4o_calculate_freq(f1, f2, rule, count_override)
@@ -241,10 +265,17 @@ def ref_binary(name: str) -> Path | None:
     return p if p.exists() else None
 
 
-def run_ref(name: str, args, cwd=None, check=False):
+def run_ref(name: str, args, cwd=None, check=False, timeout=60, attempts=3):
     """Run an unmodified reference tool from oracle/_ref; returns CompletedProcess or None."""
     exe = ref_binary(name)
     if exe is None:
         return None
-    return subprocess.run([str(exe), *map(str, args)], cwd=cwd, capture_output=True, check=check,
-                          env={**os.environ, "LC_ALL": "C"})
+    # glistmaker's main thread leaves through pthread_exit (src/glistmaker.c:365) and now and then a worker stays
+    # parked on the queue's condition variable for good: bound every run and try again
+    for attempt in range(attempts):
+        try:
+            return subprocess.run([str(exe), *map(str, args)], cwd=cwd, capture_output=True, check=check,
+                                  env={**os.environ, "LC_ALL": "C"}, timeout=timeout)
+        except subprocess.TimeoutExpired:
+            if attempt == attempts - 1:
+                raise

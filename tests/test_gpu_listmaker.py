@@ -1,0 +1,110 @@
+"""GPU parity tests of the list-building back end: gt4gpu_count_words (radix sort +
+run-length counts) through the C ABI against the oracle's restatement of wordtable_sort + merge_tables_to_file."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SORT_TILE = 512 * 12     # keys per CTA of radix_onesweep_kernel
+RLE_TILE = 512 * 8       # keys per CTA of rle_heads_kernel
+
+
+@pytest.fixture(scope="module")
+def g():
+    import genometester4_b200 as g
+    g.init(0)
+    return g
+
+
+def check(g, oracle, words, k):
+    res = g.count_words(words, k)
+    exp = oracle.count_words(words, k)
+    w, c = res.to_host()
+    assert res.n_words == len(exp.words)
+    assert res.total_count == len(words)
+    assert np.array_equal(w, exp.words)
+    assert np.array_equal(c, exp.counts)
+    res.free()
+
+
+def random_words(rng, n, k, distinct=None):
+    hi = 4 ** k
+    if distinct is None:
+        return rng.integers(0, hi, size=n, dtype=np.uint64) if hi < 2 ** 63 else \
+            rng.integers(0, 2 ** 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    pool = random_words(rng, distinct, k)
+    return pool[rng.integers(0, distinct, size=n)]
+
+
+@pytest.mark.parametrize("k", [1, 4, 11, 16, 25, 31, 32])
+def test_count_words_random(g, oracle, k):
+    rng = np.random.default_rng(100 + k)
+    for n in (1, 2, 33, SORT_TILE - 1, SORT_TILE, SORT_TILE + 1, 3 * RLE_TILE + 7, 100_003):
+        check(g, oracle, random_words(rng, n, k), k)
+
+
+def test_count_words_duplicates_and_order(g, oracle):
+    rng = np.random.default_rng(7)
+    k = 25
+    n = 5 * SORT_TILE + 123
+    check(g, oracle, np.full(n, 12345, dtype=np.uint64), k)                    # one run spanning many tiles
+    check(g, oracle, random_words(rng, n, k, distinct=3), k)
+    check(g, oracle, random_words(rng, n, k, distinct=1000), k)
+    w = np.sort(random_words(rng, n, k))
+    check(g, oracle, w, k)
+    check(g, oracle, w[::-1].copy(), k)
+    # runs that end exactly on tile boundaries of the run-length kernel
+    w = np.repeat(np.arange(10, dtype=np.uint64) * np.uint64(977), RLE_TILE)
+    check(g, oracle, rng.permutation(w), k)
+    # extreme words: 0 and 4^32 - 1
+    w = np.array([0, 2 ** 64 - 1, 0, 2 ** 64 - 1, 5, 2 ** 63, 2 ** 63], dtype=np.uint64)
+    check(g, oracle, w, 32)
+
+
+def test_count_words_empty_and_bad_args(g):
+    res = g.count_words(np.zeros(0, dtype=np.uint64), 16)
+    assert res.n_words == 0 and res.total_count == 0
+    for k in (0, 33):
+        with pytest.raises(g.GT4GPUError) as e:
+            g.count_words(np.zeros(4, dtype=np.uint64), k)
+        assert e.value.code == 1
+
+
+def test_count_words_device_input_medium(g, oracle):
+    """2e7 words already in HBM: compared with torch.unique (checker only) and, on a prefix, with the oracle."""
+    import torch
+    k = 25
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    w = torch.randint(0, 4 ** 12, (20_000_000,), generator=gen, device="cuda", dtype=torch.int64)   # ~1.2 words per key
+    torch.cuda.synchronize()
+    res = g.count_words(w.data_ptr(), k, n_words=w.numel())
+    uw, uc = torch.unique(w, return_counts=True)
+    tw, tc = res.as_torch()
+    assert res.n_words == uw.numel() and res.total_count == w.numel()
+    assert torch.equal(tw, uw) and torch.equal(tc.to(torch.int64), uc)
+    res.free()
+    check(g, oracle, w[:300_000].cpu().numpy().astype(np.uint64), k)
+
+
+def test_listmaker_pipeline_matches_glistmaker_golden(g, oracle):
+    """sequence file -> words (host reader) -> tables -> count_words -> union_multi == the list glistmaker wrote."""
+    import json
+    from pathlib import Path
+    gold_dir = Path(__file__).parent / "golden" / "maker"
+    gold = json.loads((gold_dir / "maker_golden.json").read_text())
+    for case in gold["cases"]:
+        text = (gold_dir / case["input"]).read_bytes()
+        k = case["k"]
+        words = g.sequence_words(text, k)
+        # several small tables, collated like collate_files (gt4_write_union, cutoff 1)
+        n_tables = 3
+        parts = [words[i::n_tables] for i in range(n_tables)]
+        tables = [g.count_words(p, k) for p in parts if len(p)]
+        if not tables:
+            assert case["n_words"] == 0
+            continue
+        lists = [g.WordList.from_device(*t.device_ptrs, t.n_words, k, keepalive=t) for t in tables]
+        res = g.union_multi(lists, cutoff=1)
+        assert res.n_words == case["n_words"] and res.total_count == case["total_count"]
+        import hashlib
+        assert hashlib.sha256(res.list_bytes()).hexdigest() == case["sha256"], case
