@@ -19,6 +19,10 @@ def cli_path() -> Path:
     return PKG / "gt4gpu-compare"
 
 
+def listmaker_cli_path() -> Path:
+    return PKG / "gt4gpu-listmaker"
+
+
 def build(verbose: bool = False) -> Path:
     """Compile the CUDA library and the CLI for sm_100a, in-tree (nvcc cross-compiles without a GPU)."""
     subprocess.run(["make", "-C", str(CSRC), "all"], check=True,

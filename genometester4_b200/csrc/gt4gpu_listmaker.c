@@ -1,0 +1,334 @@
+/*
+ * gt4gpu-listmaker -- drop-in for the list mode of GenomeTester4's glistmaker with the sort / count / collate
+ * back end running on a B200 through libgt4gpu (include/gt4gpu.h).
+ *
+ * Flag grammar, validation order, messages, the "<out>_<k>.list" name, tmp + rename and exit codes follow main()
+ * of /root/reference/src/glistmaker.c:138-366 (help text :1303-1326).  The pipeline mirrors the reference's tasks:
+ *
+ *   read_table      (:893-968)    sequence file -> a table of canonical words        gt4gpu_sequence_words (host)
+ *   wordtable_sort + merge_tables_to_file (:924, :1080-1144)   table -> (word, count)  gt4gpu_count_words   (GPU)
+ *   collate_files / final gt4_write_union (:787-835, :314-333)  tables -> one list     gt4gpu_union_multi   (GPU)
+ *
+ * Like the reference's list mode, -c/--cutoff/--min and --max are parsed and validated but do not filter the list
+ * (they only act on --index, :486).  Not carried over: --index, .gz inputs and "-" (stdin); they exit with status 1
+ * and a message.  --num_threads, --max_tables, --tmpdir and --stream are accepted and have nothing to steer here;
+ * --table_size is the number of words sorted per GPU table (default 2^30).
+ */
+#include <errno.h>
+#include <fcntl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <unistd.h>
+
+#include "gt4gpu.h"
+
+#define MAX_INPUTS 1024          /* glistmaker.c:141 */
+#define DEFAULT_CUTOFF 1         /* :49 */
+#define DEFAULT_NUM_THREADS 8    /* :50 */
+#define DEFAULT_NUM_TABLES (32 * 128)   /* :52 */
+#define DEFAULT_TABLE_WORDS (1ULL << 30)
+
+static int debug = 0;
+
+static void
+print_help (int exit_value)
+{
+  fprintf (stderr, "glistmaker version %u.%u.%u (%s)\n", GT4GPU_VERSION_MAJOR, GT4GPU_VERSION_MINOR, GT4GPU_VERSION_MICRO, "stable");
+  fprintf (stderr, "Usage: glistmaker <INPUTFILES> [OPTIONS]\n");
+  fprintf (stderr, "Options:\n");
+  fprintf (stderr, "    -v, --version           - print version information and exit\n");
+  fprintf (stderr, "    -h, --help              - print this usage screen and exit\n");
+  fprintf (stderr, "    -w, --wordlength NUMBER - specify index wordsize (1-32)\n");
+  fprintf (stderr, "    -o, --outputname STRING - specify output name (default \"out\")\n");
+  fprintf (stderr, "    --index                 - create index instead of list\n");
+  fprintf (stderr, "    --num_threads           - number of threads (default %u)\n", DEFAULT_NUM_THREADS);
+  fprintf (stderr, "    --max_tables            - maximum number of temporary tables (default %u)\n", DEFAULT_NUM_TABLES);
+  fprintf (stderr, "    --table_size            - maximum size of the temporary table (default %llu)\n", DEFAULT_TABLE_WORDS);
+  fprintf (stderr, "    --tmpdir                - directory for temporary files (may need an order of magnitude more space than the size of the final list)\n");
+  fprintf (stderr, "    --stream                - read files as streams instead of memory-mapping (slower but uses less virtual memory)\n");
+  fprintf (stderr, "    --index                 - creates indexed list (larger and slower)\n");
+  fprintf (stderr, "    -D                      - increase debug level\n");
+  exit (exit_value);
+}
+
+static double
+now (void)
+{
+  struct timeval tv;
+  gettimeofday (&tv, NULL);
+  return tv.tv_sec + tv.tv_usec * 1e-6;
+}
+
+/* the tables sorted so far, resident on the device */
+static gt4gpu_result tables[4096];
+static gt4gpu_list *table_lists[4096];
+static unsigned n_tables = 0;
+static double t_read = 0, t_sort = 0, t_collate = 0;
+static unsigned long long n_read = 0;
+
+static int
+flush_table (uint64_t *words, uint64_t n, unsigned wordlength)
+{
+  double t0 = now ();
+  int rc;
+  if (!n) return 0;
+  if (n_tables >= 4096) {
+    /* fold what we have into one table first (the reference collates 16 files at a time, :822-830) */
+    gt4gpu_result merged;
+    memset (&merged, 0, sizeof (merged));
+    rc = gt4gpu_union_multi ((const gt4gpu_list *const *) table_lists, n_tables, 1, GT4GPU_RULE_ADD, 1, 0, &merged);
+    if (rc) return rc;
+    for (unsigned i = 0; i < n_tables; i++) { gt4gpu_list_close (table_lists[i]); gt4gpu_result_free (&tables[i]); }
+    tables[0] = merged;
+    rc = gt4gpu_list_from_device (merged.words, merged.counts, merged.n_words, wordlength, &table_lists[0]);
+    if (rc) return rc;
+    n_tables = 1;
+  }
+  memset (&tables[n_tables], 0, sizeof (tables[0]));
+  rc = gt4gpu_count_words (words, n, 0, wordlength, &tables[n_tables]);
+  if (rc) return rc;
+  rc = gt4gpu_list_from_device (tables[n_tables].words, tables[n_tables].counts, tables[n_tables].n_words, wordlength, &table_lists[n_tables]);
+  if (rc) return rc;
+  if (debug) fprintf (stderr, "Table %u: %llu words, %llu unique\n", n_tables, (unsigned long long) n, (unsigned long long) tables[n_tables].n_words);
+  n_tables += 1;
+  t_sort += now () - t0;
+  return 0;
+}
+
+int
+main (int argc, const char *argv[])
+{
+  const char *inputs[MAX_INPUTS];
+  unsigned int n_inputs = 0, i;
+  char *end;
+  unsigned int wordlength = 0, nthreads = DEFAULT_NUM_THREADS, ntables = DEFAULT_NUM_TABLES, min = DEFAULT_CUTOFF, max = 0xffffffff;
+  unsigned long long tablesize = DEFAULT_TABLE_WORDS;
+  const char *outputname = "out";
+  int create_index = 0;
+  char tmp_name[1024], out_name[1024];
+
+  for (i = 1; i < (unsigned int) argc; i++) {
+    if (!strcmp (argv[i], "-v") || !strcmp (argv[i], "--version")) {
+      fprintf (stdout, "glistmaker version %u.%u.%u (%s)\n", GT4GPU_VERSION_MAJOR, GT4GPU_VERSION_MINOR, GT4GPU_VERSION_MICRO, "stable");
+      return 0;
+    } else if (!strcmp (argv[i], "-h") || !strcmp (argv[i], "--help") || !strcmp (argv[i], "-?")) {
+      print_help (0);
+    } else if (!strcmp (argv[i], "-o") || !strcmp (argv[i], "--outputname")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+      outputname = argv[i];
+    } else if (!strcmp (argv[i], "-w") || !strcmp (argv[i], "--wordlength")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+      wordlength = strtol (argv[i], &end, 10);
+      if (*end != 0) {
+        fprintf (stderr, "Error: Invalid word-length: %s! Must be an integer.\n", argv[i]);
+        print_help (1);
+      }
+    } else if (!strcmp (argv[i], "-c") || !strcmp (argv[i], "--cutoff") || !strcmp (argv[i], "--min")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+      min = strtol (argv[i], &end, 10);
+      if (*end != 0) {
+        fprintf (stderr, "Error: Invalid frequency cut-off: %s! Must be an integer.\n", argv[i]);
+        print_help (1);
+      }
+    } else if (!strcmp (argv[i], "--max")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+      max = strtol (argv[i], &end, 10);
+      if (*end != 0) {
+        fprintf (stderr, "Error: Invalid frequency cut-off: %s! Must be an integer.\n", argv[i]);
+        print_help (1);
+      }
+    } else if (!strcmp (argv[i], "--num_threads")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+      nthreads = strtol (argv[i], &end, 10);
+      if (*end != 0) {
+        fprintf (stderr, "Error: Invalid num-threads: %s! Must be an integer.\n", argv[i]);
+        print_help (1);
+      }
+    } else if (!strcmp (argv[i], "--max_tables")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+      ntables = strtol (argv[i], &end, 10);
+      if (*end != 0) {
+        fprintf (stderr, "Error: Invalid max_tables: %s! Must be an integer.\n", argv[i]);
+        print_help (1);
+      }
+    } else if (!strcmp (argv[i], "--table_size")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+      tablesize = strtoll (argv[i], &end, 10);
+      if (*end != 0) {
+        fprintf (stderr, "Error: Invalid table-size: %s! Must be an integer.\n", argv[i]);
+        print_help (1);
+      }
+      i += 1;     /* the reference skips the token after the value too (:214) */
+    } else if (!strcmp (argv[i], "--tmpdir")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+    } else if (!strcmp (argv[i], "--stream")) {
+      /* nothing to choose: inputs are mapped and parsed in one go */
+    } else if (!strcmp (argv[i], "--index")) {
+      create_index = 1;
+    } else if (!strcmp (argv[i], "-D")) {
+      debug += 1;
+    } else {
+      if ((argv[i][0] == '-') && argv[i][1]) print_help (1);
+      if (n_inputs >= MAX_INPUTS) continue;
+      inputs[n_inputs++] = argv[i];
+    }
+  }
+  (void) nthreads;
+  (void) ntables;
+
+  if (!n_inputs) {
+    fprintf (stderr, "Error: No FastA/FastQ file specified!\n");
+    print_help (1);
+  }
+  if (wordlength < 1 || wordlength > 32) {
+    fprintf (stderr, "Error: Invalid word-length %d (must be 1 - 32)!\n", wordlength);
+    print_help (1);
+  }
+  if (min < 1) {
+    fprintf (stderr, "Error: Invalid frequency cut-off: %d! Must be positive.\n", min);
+    print_help (1);
+  }
+  if (max < min) {
+    fprintf (stderr, "Error: Invalid frequency range: %u-%u!\n", min, max);
+    print_help (1);
+  }
+  if (strlen (outputname) > 200) {
+    fprintf (stderr, "Error: Output name exceeds the 200 character limit.");
+    return 1;
+  }
+  if (create_index) {
+    fprintf (stderr, "Error: --index is not supported by the GPU list maker\n");
+    return 1;
+  }
+  if (tablesize < 1) tablesize = 1;
+  for (i = 0; i < n_inputs; i++) {
+    struct stat s;
+    size_t len = strlen (inputs[i]);
+    if (!strcmp (inputs[i], "-") || (len > 3 && !strcmp (inputs[i] + len - 3, ".gz"))) {
+      fprintf (stderr, "Error: stdin and .gz inputs are not supported by the GPU list maker: %s\n", inputs[i]);
+      return 1;
+    }
+    if (stat (inputs[i], &s)) {
+      fprintf (stderr, "main: No such file (cannot stat): %s\n", inputs[i]);
+      exit (1);
+    }
+  }
+
+  /* read every file into tables of at most `tablesize` words; each full table is sorted and counted on the GPU */
+  uint64_t *table = NULL, table_cap = 0, table_fill = 0;
+  for (i = 0; i < n_inputs; i++) {
+    struct stat s;
+    uint64_t n_words = 0, done = 0;
+    double t0 = now ();
+    int fd = open (inputs[i], O_RDONLY);
+    if (fd < 0 || fstat (fd, &s)) {
+      fprintf (stderr, "Cannot open %s\n", inputs[i]);
+      return 1;
+    }
+    if (s.st_size == 0) { close (fd); continue; }
+    const unsigned char *text = (const unsigned char *) mmap (NULL, s.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close (fd);
+    if (text == MAP_FAILED) {
+      fprintf (stderr, "Cannot map %s\n", inputs[i]);
+      return 1;
+    }
+    uint64_t *words = (uint64_t *) malloc ((size_t) s.st_size * sizeof (uint64_t) + 8);
+    if (!words) {
+      fprintf (stderr, "Out of memory reading %s\n", inputs[i]);
+      return 1;
+    }
+    int rc = gt4gpu_sequence_words (text, (uint64_t) s.st_size, wordlength, words, (uint64_t) s.st_size, &n_words);
+    if (rc) fprintf (stderr, "fasta_reader_read_nwords: Reader %s: %s\n", inputs[i], gt4gpu_last_error ());
+    munmap ((void *) text, s.st_size);
+    t_read += now () - t0;
+    n_read += n_words;
+    while (done < n_words) {
+      uint64_t take = n_words - done;
+      if (table_fill == 0 && take >= tablesize) {
+        /* a whole table straight from the reader's buffer */
+        if ((rc = flush_table (words + done, tablesize, wordlength))) goto gpu_error;
+        done += tablesize;
+        continue;
+      }
+      if (!table) {
+        table_cap = tablesize < (1ULL << 20) ? tablesize : (1ULL << 20);
+        table = (uint64_t *) malloc (table_cap * sizeof (uint64_t));
+      }
+      if (take > tablesize - table_fill) take = tablesize - table_fill;
+      if (table_fill + take > table_cap) {
+        while (table_cap < table_fill + take) table_cap *= 2;
+        if (table_cap > tablesize) table_cap = tablesize;
+        table = (uint64_t *) realloc (table, table_cap * sizeof (uint64_t));
+      }
+      if (!table) {
+        fprintf (stderr, "Out of memory\n");
+        return 1;
+      }
+      memcpy (table + table_fill, words + done, take * sizeof (uint64_t));
+      table_fill += take;
+      done += take;
+      if (table_fill == tablesize) {
+        if ((rc = flush_table (table, table_fill, wordlength))) goto gpu_error;
+        table_fill = 0;
+      }
+    }
+    free (words);
+    continue;
+gpu_error:
+    fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
+    return 1;
+  }
+  if (table_fill) {
+    if (flush_table (table, table_fill, wordlength)) {
+      fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
+      return 1;
+    }
+  }
+  free (table);
+
+  snprintf (tmp_name, sizeof (tmp_name), "%s_%u.list.tmp", outputname, wordlength);
+  snprintf (out_name, sizeof (out_name), "%s_%u.list", outputname, wordlength);
+  int ofile = open (tmp_name, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+  if (ofile < 0) {
+    fprintf (stderr, "Cannot create output file %s\n", tmp_name);
+    exit (1);
+  }
+  double t0 = now ();
+  int rc = 0;
+  if (n_tables > 0) {
+    /* final collation (gt4_write_union with cutoff 1, :314-333) */
+    gt4gpu_header header;
+    rc = gt4gpu_write_union ((const gt4gpu_list *const *) table_lists, n_tables, 1, ofile, &header);
+    if (debug) fprintf (stderr, "Words %llu, unique %llu\n", (unsigned long long) header.total_count, (unsigned long long) header.n_words);
+  } else {
+    gt4gpu_header header;
+    gt4gpu_header_init (&header, wordlength);
+    if (write (ofile, &header, sizeof (header)) != (ssize_t) sizeof (header)) rc = GT4GPU_ERR_IO;
+  }
+  close (ofile);
+  t_collate = now () - t0;
+  if (rc) {
+    fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
+    unlink (tmp_name);
+    return 1;
+  }
+  if (rename (tmp_name, out_name)) {
+    fprintf (stderr, "Cannot rename %s to %s\n", tmp_name, out_name);
+  }
+  if (debug) {
+    fprintf (stderr, "Read %llu words at %.2f (%u words/s)\n", n_read, t_read, (unsigned int) (n_read / (t_read > 0 ? t_read : 1e-9)));
+    fprintf (stderr, "Sort %llu words at %.2f (%u words/s)\n", n_read, t_sort, (unsigned int) (n_read / (t_sort > 0 ? t_sort : 1e-9)));
+    fprintf (stderr, "Collate and write %u tables at %.2f\n", n_tables, t_collate);
+  }
+  for (i = 0; i < n_tables; i++) {
+    gt4gpu_list_close (table_lists[i]);
+    gt4gpu_result_free (&tables[i]);
+  }
+  gt4gpu_shutdown ();
+  return 0;
+}

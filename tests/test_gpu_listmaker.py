@@ -108,3 +108,35 @@ def test_listmaker_pipeline_matches_glistmaker_golden(g, oracle):
         assert res.n_words == case["n_words"] and res.total_count == case["total_count"]
         import hashlib
         assert hashlib.sha256(res.list_bytes()).hexdigest() == case["sha256"], case
+
+
+def test_listmaker_cli_against_glistmaker_golden(tmp_path):
+    """gt4gpu-listmaker leaves byte for byte the <out>_<k>.list the unmodified glistmaker wrote (committed digests);
+    small --table_size values force many GPU tables and the final collation."""
+    import hashlib
+    import json
+    import subprocess
+    from pathlib import Path
+    from genometester4_b200 import _lib
+    gold_dir = Path(__file__).parent / "golden" / "maker"
+    gold = json.loads((gold_dir / "maker_golden.json").read_text())
+    for i, case in enumerate(gold["cases"]):
+        if i % 2 and case["k"] not in (1, 32):
+            continue
+        # "--table_size N" swallows the token after N as well (src/glistmaker.c:214), hence the filler
+        extra = [[], ["--table_size", "1000", "filler"], ["--table_size", "37", "filler", "-D"]][i % 3]
+        r = subprocess.run([str(_lib.listmaker_cli_path()), str(gold_dir / case["input"]), "-w", str(case["k"]), "-o", "t", *extra],
+                           cwd=tmp_path, capture_output=True)
+        assert r.returncode == 0, (case, r.stderr)
+        data = (tmp_path / f"t_{case['k']}.list").read_bytes()
+        assert len(data) == case["bytes"] and hashlib.sha256(data).hexdigest() == case["sha256"], (case, extra)
+        assert not (tmp_path / f"t_{case['k']}.list.tmp").exists()
+        (tmp_path / f"t_{case['k']}.list").unlink()
+    # several input files = one list of their words together
+    r = subprocess.run([str(_lib.listmaker_cli_path()), str(gold_dir / "plain.fa"), str(gold_dir / "multi.fa"), str(gold_dir / "reads.fq"),
+                        "-w", "16", "-o", "all", "--table_size", "5000", "x"], cwd=tmp_path, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    from oracle import oracle as O
+    words = np.concatenate([O.sequence_words((gold_dir / f).read_bytes(), 16) for f in ("plain.fa", "multi.fa", "reads.fq")])
+    exp = O.count_words(words, 16)
+    assert (tmp_path / "all_16.list").read_bytes() == O.header_bytes(16, len(exp.words), int(exp.counts.sum())) + exp.records().tobytes()

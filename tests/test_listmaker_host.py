@@ -69,3 +69,47 @@ def test_host_sequence_reader_errors(oracle):
     with pytest.raises(g.GT4GPUError) as e:
         g.sequence_words(b">a\nACGT\n", 33)
     assert e.value.code == 1
+
+
+# ---- gt4gpu-listmaker: flag grammar and validation (no device needed before the first table is sorted)
+
+MAKER_CASES = [
+    [],
+    ["-v"], ["--version"], ["-h"],
+    ["plain.fa"],
+    ["plain.fa", "-w", "0"], ["plain.fa", "-w", "33"], ["plain.fa", "-w", "1x"],
+    ["plain.fa", "-w", "16", "-c", "0"], ["plain.fa", "-w", "16", "-c", "5", "--max", "2"],
+    ["plain.fa", "-w", "16", "--bogus"],
+    ["plain.fa", "-w", "16", "-o", "x" * 201],
+    ["nosuch.fa", "-w", "16"],
+    ["-w", "16"],
+]
+
+
+@pytest.mark.parametrize("args", MAKER_CASES, ids=lambda a: " ".join(a)[:40] or "noargs")
+def test_listmaker_cli_validation_matches_reference(args, oracle):
+    import subprocess
+    from genometester4_b200 import _lib
+    cli = _lib.listmaker_cli_path()
+    assert cli.exists(), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    mine = subprocess.run([str(cli), *args], cwd=GOLD_DIR, capture_output=True)
+    if oracle.ref_binary("glistmaker") is None:
+        pytest.skip("oracle/_ref not built")
+    ref = oracle.run_ref("glistmaker", args, cwd=GOLD_DIR, timeout=10)
+    assert mine.returncode == ref.returncode, (mine.stderr, ref.stderr)
+    assert mine.stdout == ref.stdout
+    # the usage text differs in one line (the default table size is a GPU table here)
+    strip = lambda b: b"\n".join(l for l in b.split(b"\n") if b"--table_size" not in l)
+    assert strip(mine.stderr) == strip(ref.stderr)
+
+
+def test_listmaker_cli_static_expectations():
+    import subprocess
+    from genometester4_b200 import _lib
+    cli = _lib.listmaker_cli_path()
+    r = subprocess.run([str(cli), "-v"], capture_output=True)
+    assert r.returncode == 0 and r.stdout == b"glistmaker version 4.2.16 (stable)\n"
+    r = subprocess.run([str(cli), "plain.fa", "-w", "40"], cwd=GOLD_DIR, capture_output=True)
+    assert r.returncode == 1 and r.stderr.startswith(b"Error: Invalid word-length 40 (must be 1 - 32)!\n")
+    r = subprocess.run([str(cli), "plain.fa", "-w", "16", "--index"], cwd=GOLD_DIR, capture_output=True)
+    assert r.returncode == 1 and b"not supported" in r.stderr
