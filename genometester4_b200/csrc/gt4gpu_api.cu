@@ -1212,7 +1212,7 @@ int gt4gpu_count_words (const uint64_t *words, uint64_t n_words, int on_device, 
   if ((rc = dev_alloc (&tmp.p[4], rle_scratch_bytes (n)))) return rc;
   first = (uint64_t *) tmp.p[3]; ws_rle = (unsigned char *) tmp.p[4];
   unsigned long long *d_unique = nullptr;
-  CU (launch_rle_heads (sorted, n, words_tmp, first, ws_rle, &d_unique, st));
+  CU (launch_rle_heads (sorted, n, words_tmp, first, ws_rle, g_ctx.sm_count, &d_unique, st));
   unsigned long long n_unique = 0;
   CU (cudaMemcpyAsync (&n_unique, d_unique, sizeof (n_unique), cudaMemcpyDeviceToHost, st));
   CU (cudaStreamSynchronize (st));

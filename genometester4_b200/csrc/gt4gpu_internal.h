@@ -77,7 +77,7 @@ cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_
                                uint64_t **sorted, cudaStream_t st);
 size_t rle_scratch_bytes (uint64_t n);
 cudaError_t launch_rle_heads (const uint64_t *sorted, uint64_t n, uint64_t *words_tmp, uint64_t *first, unsigned char *scratch,
-                              unsigned long long **d_n_unique, cudaStream_t st);
+                              int sm_count, unsigned long long **d_n_unique, cudaStream_t st);
 cudaError_t launch_rle_counts (const uint64_t *words_tmp, const uint64_t *first, uint64_t n_unique, uint64_t n,
                                uint64_t *words, uint32_t *counts, cudaStream_t st);
 

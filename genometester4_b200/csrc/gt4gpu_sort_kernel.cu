@@ -81,7 +81,17 @@ radix_hist_kernel (const uint64_t *__restrict__ keys, uint64_t n, int n_pass, un
   const uint64_t per_cta = (n + gridDim.x - 1) / gridDim.x;
   const uint64_t lo = per_cta * blockIdx.x;
   const uint64_t hi = lo + per_cta < n ? lo + per_cta : n;
-  for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+  constexpr int U = 4;         // independent loads in flight per thread
+  uint64_t i = lo + threadIdx.x;
+  for (; i + (U - 1) * (uint64_t) blockDim.x < hi; i += U * (uint64_t) blockDim.x) {
+    uint64_t key[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) key[u] = keys[i + u * (uint64_t) blockDim.x];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      for (int p = 0; p < n_pass; p++) atomicAdd (&mine[p][(key[u] >> (8 * p)) & 255u], 1u);
+  }
+  for (; i < hi; i += blockDim.x) {
     const uint64_t key = keys[i];
     for (int p = 0; p < n_pass; p++) atomicAdd (&mine[p][(key >> (8 * p)) & 255u], 1u);
   }
@@ -272,16 +282,33 @@ radix_onesweep_kernel (const SweepArgs a)
 // ------------------------------------------------------------------------------------------
 // run-length encoding of the sorted keys
 // ------------------------------------------------------------------------------------------
-constexpr int RLE_NT = 512;
+#ifndef GT4_RLE_NT
+#define GT4_RLE_NT 128
+#endif
+#ifndef GT4_RLE_ITEMS
+#define GT4_RLE_ITEMS 16
+#endif
+#ifndef GT4_RLE_MIN_CTAS
+#define GT4_RLE_MIN_CTAS 6
+#endif
+constexpr int RLE_NT = GT4_RLE_NT;
 constexpr int RLE_WARPS = RLE_NT / 32;
-constexpr int RLE_ITEMS = 8;
+constexpr int RLE_ITEMS = GT4_RLE_ITEMS;
 constexpr int RLE_TILE = RLE_NT * RLE_ITEMS;
 
 constexpr uint64_t DESC_PARTIAL = 1ull << 62;
 constexpr uint64_t DESC_INCLUSIVE = 2ull << 62;
 constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1;
 
-// all 32 lanes of one warp; exclusive prefix of `aggregate` over the tiles
+// All 32 lanes of one warp; exclusive prefix of `aggregate` over the tiles.  One hop inspects RLE_LB_W rows of 32
+// descriptors (row k, lane l -> tile pred - 32 k - l), nearest first: with several hundred tiles in flight the nearest
+// tile that already knows its prefix is often more than 32 tiles back, and every hop costs an L2 round trip.  Only a
+// descriptor nearer than the nearest inclusive one can make the warp wait, and then only its row is polled again.
+#ifndef GT4_RLE_LB_W
+#define GT4_RLE_LB_W 4
+#endif
+constexpr int RLE_LB_W = GT4_RLE_LB_W;
+
 __device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t tile, uint64_t aggregate, int lane)
 {
   if (tile == 0) {
@@ -289,36 +316,51 @@ __device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t
     return 0;
   }
   if (lane == 0) st_relaxed (desc + tile, DESC_PARTIAL | aggregate);
-  uint64_t exclusive = 0;
-  int64_t pred = (int64_t) tile - 1;
-  while (true) {
-    const int64_t idx = pred - lane;
-    uint64_t d = (idx >= 0) ? ld_relaxed (desc + idx) : DESC_INCLUSIVE;
-    while (__any_sync (0xffffffffu, (d >> 62) == 0)) {
-      if ((d >> 62) == 0) d = ld_relaxed (desc + idx);
+  uint64_t lane_sum = 0;
+  int64_t pred = (int64_t) tile - 1 - lane;
+  bool done = false;
+  while (!done) {
+    uint64_t d[RLE_LB_W];
+#pragma unroll
+    for (int k = 0; k < RLE_LB_W; k++) d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
+#pragma unroll
+    for (int k = 0; k < RLE_LB_W; k++) {
+      if (done) break;
+      while (true) {
+        const uint32_t st = (uint32_t) (d[k] >> 62);
+        const uint32_t m_wait = __ballot_sync (0xffffffffu, st == 0);
+        const uint32_t m_incl = __ballot_sync (0xffffffffu, st == 2);
+        const uint32_t m_stop = m_wait | m_incl;
+        if (m_stop == 0) {                     // a full row of partial counts
+          lane_sum += d[k] & DESC_VALUE_MASK;
+          break;
+        }
+        const int first = __ffs (m_stop) - 1;
+        if ((m_wait >> first) & 1u) {          // the nearest stopper has not posted yet: poll this row again
+          d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
+          continue;
+        }
+        if (lane <= first) lane_sum += d[k] & DESC_VALUE_MASK;
+        done = true;
+        break;
+      }
     }
-    const uint32_t incl = __ballot_sync (0xffffffffu, (d >> 62) == 2);
-    if (incl) {
-      const int first = __ffs (incl) - 1;
-      exclusive += warp_sum_u64 (lane <= first ? (d & DESC_VALUE_MASK) : 0ull);
-      break;
-    }
-    exclusive += warp_sum_u64 (d & DESC_VALUE_MASK);
-    pred -= 32;
+    pred -= 32 * RLE_LB_W;
   }
+  const uint64_t exclusive = warp_sum_u64 (lane_sum);
   if (lane == 0) st_relaxed (desc + tile, DESC_INCLUSIVE | (exclusive + aggregate));
   return exclusive;
 }
 
-__global__ void __launch_bounds__ (RLE_NT)
+__global__ void __launch_bounds__ (RLE_NT, GT4_RLE_MIN_CTAS)
 rle_heads_kernel (const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ words, uint64_t *__restrict__ first,
-                  uint64_t *desc, uint32_t *ticket, unsigned long long *n_unique)
+                  uint64_t *desc, uint32_t *ticket, unsigned long long *n_unique, int debug)
 {
   __shared__ uint32_t s_wcnt[RLE_WARPS];
   __shared__ uint64_t s_base;
   __shared__ uint32_t s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd (ticket, 1u);
+  if (tid == 0) s_tile = (debug & 32) ? blockIdx.x : atomicAdd (ticket, 1u);
   __syncthreads ();
   const uint64_t tile = s_tile;
   const uint64_t base = tile * RLE_TILE + (uint64_t) warp * 32 * RLE_ITEMS;
@@ -354,7 +396,7 @@ rle_heads_kernel (const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__res
     }
     const uint32_t tile_cnt = __shfl_sync (0xffffffffu, incl, RLE_WARPS - 1);
     if (lane < RLE_WARPS) s_wcnt[lane] = incl - v;
-    const uint64_t excl = lookback_exclusive (desc, tile, tile_cnt, lane);
+    const uint64_t excl = (debug & 16) ? tile * RLE_TILE : lookback_exclusive (desc, tile, tile_cnt, lane);
     if (lane == 0) {
       s_base = excl;
       if ((tile + 1) * RLE_TILE >= n) *n_unique = excl + tile_cnt;     // the last tile knows the total
@@ -451,7 +493,7 @@ size_t rle_scratch_bytes (uint64_t n)
 
 // sorted keys -> words_tmp[u], first[u] for every run u; *d_n_unique (device, u64) receives the number of runs
 cudaError_t launch_rle_heads (const uint64_t *sorted, uint64_t n, uint64_t *words_tmp, uint64_t *first, unsigned char *scratch,
-                              unsigned long long **d_n_unique, cudaStream_t st)
+                              int sm_count, unsigned long long **d_n_unique, cudaStream_t st)
 {
   *d_n_unique = reinterpret_cast<unsigned long long *> (scratch);
   cudaError_t e = cudaMemsetAsync (scratch, 0, rle_scratch_bytes (n), st);
@@ -460,7 +502,9 @@ cudaError_t launch_rle_heads (const uint64_t *sorted, uint64_t n, uint64_t *word
   if (n_tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   uint32_t *ticket = reinterpret_cast<uint32_t *> (scratch + 8);
   uint64_t *desc = reinterpret_cast<uint64_t *> (scratch + 256);
-  rle_heads_kernel<<<(unsigned) n_tiles, RLE_NT, 0, st>>> (sorted, n, words_tmp, first, desc, ticket, *d_n_unique);
+  (void) sm_count;     // one CTA per tile: a persistent loop over tickets measured slower (the next CTA's loads overlap the stores)
+  rle_heads_kernel<<<(unsigned) n_tiles, RLE_NT, 0, st>>> (sorted, n, words_tmp, first, desc, ticket, *d_n_unique,
+                                                         getenv ("GT4GPU_DEBUG") ? atoi (getenv ("GT4GPU_DEBUG")) : 0);
   return cudaGetLastError ();
 }
 

@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 SORT_TILE = 512 * 12     # keys per CTA of radix_onesweep_kernel
-RLE_TILE = 512 * 8       # keys per CTA of rle_heads_kernel
+RLE_TILE = 128 * 16      # keys per CTA of rle_heads_kernel
 
 
 @pytest.fixture(scope="module")
