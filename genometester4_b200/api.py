@@ -272,6 +272,23 @@ def gt4_write_union(arrays, cutoff: int, ofile: int = 0) -> Header:
     return h
 
 
+def lookup(lst: WordList, queries, canonize: bool = True):
+    """Batch form of glistquery's exact lookups (search_one_word, src/glistquery.c:544-568, over word_map_lookup,
+    src/word-map.c:134-163).  Returns (canonical words, counts) as numpy arrays; count 0 = the list does not hold it."""
+    q = np.ascontiguousarray(queries, dtype=np.uint64)
+    counts = np.zeros(q.size, dtype=np.uint32)
+    canon = np.zeros(q.size, dtype=np.uint64)
+    _check(_lib.load().gt4gpu_lookup(lst._h, C.c_void_p(q.ctypes.data), q.size, 0, int(bool(canonize)),
+                                     C.c_void_p(counts.ctypes.data), C.c_void_p(canon.ctypes.data)))
+    return canon, counts
+
+
+def lookup_device(lst: WordList, queries_ptr: int, n_queries: int, counts_ptr: int, canonical_ptr: int = 0, canonize: bool = True) -> None:
+    """Same on device arrays (``tensor.data_ptr()``)."""
+    _check(_lib.load().gt4gpu_lookup(lst._h, C.c_void_p(queries_ptr), n_queries, 1, int(bool(canonize)),
+                                     C.c_void_p(counts_ptr), C.c_void_p(canonical_ptr) if canonical_ptr else None))
+
+
 def sequence_words(text: bytes, word_length: int) -> np.ndarray:
     """Canonical words of a FastA/FastQ image in file order (fasta_reader_read_nwords, src/fasta.c:88-290).  Host only.
     Raises GT4GPUError(code 3) where the reference's reader reports a format error."""

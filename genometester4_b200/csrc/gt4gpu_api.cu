@@ -1071,6 +1071,37 @@ int gt4gpu_union_matrix (const gt4gpu_list *const *lists, unsigned n_lists, int 
 
 // ------------------------------------------------------------------ results
 
+// ------------------------------------------------------------------ lookups
+
+int gt4gpu_lookup (const gt4gpu_list *list, const uint64_t *queries, uint64_t n_queries, int on_device, int canonize,
+                   uint32_t *counts_out, uint64_t *canonical_out)
+{
+  if (!list || !counts_out || (!queries && n_queries)) return fail (GT4GPU_ERR_ARG, "null argument");
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  if (n_queries == 0) return 0;
+  cudaStream_t st = g_ctx.stream;
+  if (on_device) {
+    CU (launch_lookup (list->words, list->counts, list->n_words, list->word_length, canonize, queries, n_queries, canonical_out, counts_out, st));
+    CU (cudaStreamSynchronize (st));
+    return 0;
+  }
+  struct Scratch {
+    void *p[3] = {nullptr, nullptr, nullptr};
+    ~Scratch () { for (void *q : p) dev_free (q); }
+  } tmp;
+  if ((rc = dev_alloc (&tmp.p[0], n_queries * sizeof (uint64_t)))) return rc;
+  if ((rc = dev_alloc (&tmp.p[1], n_queries * sizeof (uint32_t)))) return rc;
+  if (canonical_out && (rc = dev_alloc (&tmp.p[2], n_queries * sizeof (uint64_t)))) return rc;
+  CU (cudaMemcpyAsync (tmp.p[0], queries, n_queries * sizeof (uint64_t), cudaMemcpyHostToDevice, st));
+  CU (launch_lookup (list->words, list->counts, list->n_words, list->word_length, canonize, (const uint64_t *) tmp.p[0], n_queries,
+                     (uint64_t *) tmp.p[2], (uint32_t *) tmp.p[1], st));
+  CU (cudaMemcpyAsync (counts_out, tmp.p[1], n_queries * sizeof (uint32_t), cudaMemcpyDeviceToHost, st));
+  if (canonical_out) CU (cudaMemcpyAsync (canonical_out, tmp.p[2], n_queries * sizeof (uint64_t), cudaMemcpyDeviceToHost, st));
+  CU (cudaStreamSynchronize (st));
+  return 0;
+}
+
 // ------------------------------------------------------------------ list building
 
 // Host-side reader of FastA / FastQ images (fasta_reader_read_nwords, src/fasta.c:88-290, with canonize = 1 as

@@ -69,6 +69,10 @@ cudaError_t launch_index16 (const void *records, uint64_t n, int has_next, uint6
 cudaError_t launch_scatter_counts (const uint64_t *rows, uint64_t n_rows, const uint64_t *words, const uint32_t *counts,
                                    uint64_t n, unsigned j, unsigned n_lists, uint32_t *matrix, cudaStream_t st);
 
+// counts_out[i] = count of queries[i] (canonical form when canonize) in the list, 0 when absent
+cudaError_t launch_lookup (const uint64_t *words, const uint32_t *counts, uint64_t n, unsigned k, int canonize,
+                           const uint64_t *queries, uint64_t n_queries, uint64_t *canonical_out, uint32_t *counts_out, cudaStream_t st);
+
 // ---- list building (gt4gpu_sort_kernel.cu): least-significant-digit radix sort of raw words + run-length counts
 static constexpr int SORT_MAX_PASSES = 8;                                        // 8-bit digits of a 64-bit word
 static constexpr size_t SORT_SCRATCH_HEAD = 2 * SORT_MAX_PASSES * 256 * 8 + 256;  // histograms, bin starts, tickets

@@ -482,6 +482,55 @@ cudaError_t launch_index16 (const void *records, uint64_t n, int has_next, uint6
   return cudaGetLastError ();
 }
 
+// ------------------------------------------------------------------------------------------
+// batch lookups (word_map_lookup, src/word-map.c:134-163, for many words at once)
+// ------------------------------------------------------------------------------------------
+// 2-bit reverse complement of a k-mer word (get_reverse_complement, src/sequence.c:65-79), without the loop:
+// complement, reverse the 32 two-bit groups of the 64-bit word, shift the k groups back down
+__device__ __forceinline__ uint64_t reverse_complement (uint64_t w, unsigned k)
+{
+  w = ~w;
+  w = ((w >> 2) & 0x3333333333333333ull) | ((w & 0x3333333333333333ull) << 2);
+  w = ((w >> 4) & 0x0f0f0f0f0f0f0f0full) | ((w & 0x0f0f0f0f0f0f0f0full) << 4);
+  w = __byte_perm ((uint32_t) (w >> 32), 0, 0x0123) | ((uint64_t) __byte_perm ((uint32_t) w, 0, 0x0123) << 32);
+  return w >> (64 - 2 * k);
+}
+
+__global__ void __launch_bounds__ (256)
+lookup_kernel (const uint64_t *__restrict__ words, const uint32_t *__restrict__ counts, uint64_t n, unsigned k, int canonize,
+               const uint64_t *__restrict__ queries, uint64_t n_queries, uint64_t *__restrict__ canonical_out,
+               uint32_t *__restrict__ counts_out)
+{
+  const uint64_t q = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  uint64_t w = queries[q];
+  if (canonize) {
+    const uint64_t r = reverse_complement (w, k);
+    if (r < w) w = r;
+  }
+  // lower bound; the upper levels of the search stay in L2 across the batch
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg (words + mid) < w) lo = mid + 1;
+    else hi = mid;
+  }
+  uint32_t c = 0;
+  if (lo < n && __ldg (words + lo) == w) c = __ldg (counts + lo);
+  if (canonical_out) canonical_out[q] = w;
+  counts_out[q] = c;
+}
+
+cudaError_t launch_lookup (const uint64_t *words, const uint32_t *counts, uint64_t n, unsigned k, int canonize,
+                           const uint64_t *queries, uint64_t n_queries, uint64_t *canonical_out, uint32_t *counts_out, cudaStream_t st)
+{
+  if (n_queries == 0) return cudaSuccess;
+  const uint64_t grid = (n_queries + 255) / 256;
+  if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  lookup_kernel<<<(unsigned) grid, 256, 0, st>>> (words, counts, n, k, canonize, queries, n_queries, canonical_out, counts_out);
+  return cudaGetLastError ();
+}
+
 cudaError_t launch_scatter_counts (const uint64_t *rows, uint64_t n_rows, const uint64_t *words, const uint32_t *counts,
                                    uint64_t n, unsigned j, unsigned n_lists, uint32_t *matrix, cudaStream_t st)
 {

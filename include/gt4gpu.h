@@ -177,6 +177,19 @@ int gt4gpu_write_union (const gt4gpu_list *const *lists, unsigned n_lists, uint3
 int gt4gpu_union_matrix (const gt4gpu_list *const *lists, unsigned n_lists, int is_union,
                          uint64_t *words, uint32_t *counts, uint64_t max_rows, uint64_t *n_rows);
 
+/* ---- lookups (the step after the merge) ------------------ */
+
+/* Replaces word_map_lookup (binary search, src/word-map.c:134-163) for a batch of words, the way glistquery's
+ * search_one_word drives it without mismatches (src/glistquery.c:544-568): when canonize is non-zero every query is
+ * first replaced by the smaller of itself and its reverse complement (get_reverse_complement, src/sequence.c:65-79)
+ * and that word is stored in canonical_out (may be NULL); counts_out[i] = the list's count of the word, 0 when the list
+ * does not hold it (the reference prints "<word>\t0" then).  queries / outputs are all HOST (on_device = 0) or all
+ * DEVICE arrays.  The list-against-list zipper (search_list_zipper, src/glistquery.c:702-717) needs no entry point of
+ * its own: it is gt4gpu_compare2 (query_list, list, GT4GPU_OP_INTRSEC, GT4GPU_RULE_FIRST, cutoff 0), and
+ * search_lists_multi (:776-812) is gt4gpu_union_matrix with is_union = 1. */
+int gt4gpu_lookup (const gt4gpu_list *list, const uint64_t *queries, uint64_t n_queries, int on_device, int canonize,
+                   uint32_t *counts_out, uint64_t *canonical_out);
+
 /* ---- list building (the step before the merge) ----------- */
 
 /* Replaces fasta_reader_read_nwords (src/fasta.c:88-290) as glistmaker drives it (read_table, src/glistmaker.c:922;

@@ -208,6 +208,25 @@ def count_words(words, word_length: int) -> SList:
     return SList(ow[:u].copy(), oc[:u].copy(), word_length)
 
 
+def lookup(lst: "SList", queries, canonize: bool = True):
+    """(canonical words, counts) of a batch of query words: search_one_word with no mismatches
+    (src/glistquery.c:544-568) over word_map_lookup (src/word-map.c:134-163); count 0 = not in the list."""
+    q = np.ascontiguousarray(queries, dtype=np.uint64)
+    w = np.ascontiguousarray(lst.words, dtype=np.uint64)
+    c = np.ascontiguousarray(lst.counts, dtype=np.uint32)
+    ow = np.empty(max(1, q.size), dtype=np.uint64)
+    oc = np.empty(max(1, q.size), dtype=np.uint32)
+    lib().gt4o_lookup(C.c_void_p(w.ctypes.data), C.c_void_p(c.ctypes.data), C.c_uint64(w.size), C.c_uint(lst.word_length),
+                      C.c_void_p(q.ctypes.data), C.c_uint64(q.size), C.c_int(int(canonize)), C.c_void_p(ow.ctypes.data),
+                      C.c_void_p(oc.ctypes.data))
+    return ow[:q.size].copy(), oc[:q.size].copy()
+
+
+def word_to_string(word: int, word_length: int) -> str:
+    """src/sequence.c:88-100"""
+    return "".join("ACGT"[(int(word) >> (2 * (word_length - 1 - i))) & 3] for i in range(word_length))
+
+
 def calculate_freq(f1, f2, rule, count_override=1):
     rule = RULES[rule] if isinstance(rule, str) else int(rule)
     return lib().gt4o_calculate_freq(f1, f2, rule, count_override)

@@ -1,0 +1,80 @@
+"""GPU parity tests of the lookup row through the C ABI: gt4gpu_lookup against the
+oracle and the committed glistquery output; the zipper as gt4gpu_compare2 (intersection, rule first)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests.test_query_host import GOLD, GOLD_DIR, lines, read_queries
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g():
+    import genometester4_b200 as g
+    g.init(0)
+    return g
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"k{c['k']}")
+def test_lookup_matches_glistquery_golden(case, g, oracle):
+    k = case["k"]
+    main = g.WordList.open(GOLD_DIR / f"main_{k}.list")
+    canon, counts = g.lookup(main, read_queries(k))
+    assert lines(oracle, canon, counts, k) == (GOLD_DIR / f"lookup_{k}.out").read_bytes()
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"k{c['k']}")
+def test_zipper_matches_glistquery_golden(case, g, oracle):
+    k = case["k"]
+    main = g.WordList.open(GOLD_DIR / f"main_{k}.list")
+    sub = g.WordList.open(GOLD_DIR / f"sub_{k}.list")
+    res = g.compare_wordmaps(sub, main, find_intrsec=1, rule=g.RULE_FIRST, cutoff=0)["intrsec"]
+    w, c = res.to_host()
+    assert lines(oracle, w, c, k) == (GOLD_DIR / f"zipper_{k}.out").read_bytes()
+
+
+@pytest.mark.parametrize("k,n,nq", [(1, 3, 50), (9, 50_000, 200_000), (25, 1_000_000, 3_000_000), (32, 300_000, 500_000)])
+def test_lookup_random_vs_oracle(k, n, nq, g, oracle):
+    rng = np.random.default_rng(k)
+    hi = min(4 ** k, 2 ** 63)
+    words = np.unique(rng.integers(0, hi, size=n, dtype=np.uint64))
+    counts = rng.integers(1, 2 ** 32, size=words.size, dtype=np.uint64).astype(np.uint32)
+    lst = oracle.SList(words, counts, k)
+    q = np.concatenate([rng.choice(words, size=nq // 2), rng.integers(0, hi, size=nq - nq // 2, dtype=np.uint64)])
+    gl = g.WordList.from_arrays(words, counts, k)
+    for canonize in (True, False):
+        cw, cc = g.lookup(gl, q, canonize=canonize)
+        ow, oc = oracle.lookup(lst, q, canonize=canonize)
+        assert np.array_equal(cw, ow) and np.array_equal(cc, oc)
+    assert (cc > 0).sum() >= nq // 2
+
+
+def test_lookup_edges(g, oracle):
+    empty = g.WordList.from_arrays(np.zeros(0, np.uint64), np.zeros(0, np.uint32), 16)
+    cw, cc = g.lookup(empty, np.array([0, 5, 2 ** 32 - 1], dtype=np.uint64))
+    assert not cc.any()
+    one = g.WordList.from_arrays(np.array([2 ** 64 - 1], np.uint64), np.array([7], np.uint32), 32)
+    cw, cc = g.lookup(one, np.array([2 ** 64 - 1, 0, 2 ** 64 - 2], dtype=np.uint64), canonize=False)
+    assert cc.tolist() == [7, 0, 0]
+    cw, cc = g.lookup(one, np.zeros(0, dtype=np.uint64))
+    assert cc.size == 0
+
+
+def test_lookup_device_arrays(g, oracle):
+    import torch
+    k = 20
+    rng = np.random.default_rng(3)
+    words = np.unique(rng.integers(0, 4 ** k, size=200_000, dtype=np.uint64))
+    counts = rng.integers(1, 100, size=words.size).astype(np.uint32)
+    gl = g.WordList.from_arrays(words, counts, k)
+    q = torch.from_numpy(np.concatenate([rng.choice(words, 100_000), rng.integers(0, 4 ** k, 100_000, dtype=np.uint64)]).astype(np.int64)).cuda()
+    out = torch.empty(q.numel(), dtype=torch.int32, device="cuda")
+    canon = torch.empty(q.numel(), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    g.lookup_device(gl, q.data_ptr(), q.numel(), out.data_ptr(), canon.data_ptr())
+    ow, oc = oracle.lookup(oracle.SList(words, counts, k), q.cpu().numpy().astype(np.uint64))
+    assert np.array_equal(out.cpu().numpy().astype(np.uint32), oc)
+    assert np.array_equal(canon.cpu().numpy().astype(np.uint64), ow)
