@@ -8,7 +8,7 @@ the built library and a CUDA device.
 """
 from .api import (  # noqa: F401
     GT4GPUError, Result, WordList, compare_wordmaps, gt4_is_union, gt4_union, gt4_write_union,
-    count_words, init, intersect_multi, last_timing, lookup, lookup_device, plan_splitters, sequence_words, set_option, set_stream, set_tile,
+    count_words, fasta_words_device, init, intersect_multi, last_timing, lookup, lookup_device, plan_splitters, sequence_words, set_option, set_stream, set_tile,
     union_multi,
 )
 from .api import RULE_ADD, RULE_DEFAULT, RULE_FIRST, RULE_MAX, RULE_MIN, RULE_NUMBER, RULE_SECOND, RULE_SUBTRACT  # noqa: F401

@@ -73,6 +73,8 @@ SIGNATURES = {
     "gt4gpu_union_matrix": (_I, [C.POINTER(_P), C.c_uint, _I, _P, _P, _U64, C.POINTER(_U64)]),
     "gt4gpu_lookup": (_I, [_P, _P, _U64, _I, _I, _P, _P]),
     "gt4gpu_sequence_words": (_I, [_P, _U64, _U32, _P, _U64, C.POINTER(_U64)]),
+    "gt4gpu_fasta_words_device": (_I, [_P, _U64, _U32, C.POINTER(_P), C.POINTER(_U64)]),
+    "gt4gpu_device_free": (None, [_P]),
     "gt4gpu_count_words": (_I, [_P, _U64, _I, _U32, C.POINTER(CResult)]),
     "gt4gpu_result_to_host_soa": (_I, [C.POINTER(CResult), _P, _P]),
     "gt4gpu_result_to_host_aos": (_I, [C.POINTER(CResult), _P]),

@@ -298,6 +298,42 @@ def sequence_words(text: bytes, word_length: int) -> np.ndarray:
     return out[:n.value].copy()
 
 
+class DeviceWords:
+    """Canonical words of a FastA image, resident in HBM (gt4gpu_fasta_words_device)."""
+
+    def __init__(self, ptr: int, n: int, word_length: int):
+        self.ptr, self.n_words, self.word_length = ptr, n, word_length
+
+    def to_host(self) -> np.ndarray:
+        import torch
+
+        class _View:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+        if not self.n_words:
+            return np.zeros(0, dtype=np.uint64)
+        return torch.as_tensor(_View(self.ptr, self.n_words), device="cuda").cpu().numpy().astype(np.uint64)
+
+    def free(self):
+        if self.ptr:
+            _lib.load().gt4gpu_device_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fasta_words_device(text: bytes, word_length: int) -> DeviceWords:
+    """FastA image (host bytes) -> canonical words in HBM, parsed on the GPU (fasta_reader_read_nwords,
+    src/fasta.c:88-290).  Feed ``.ptr`` / ``.n_words`` to :func:`count_words`."""
+    ptr, n = C.c_void_p(), C.c_uint64()
+    _check(_lib.load().gt4gpu_fasta_words_device(text, len(text), word_length, C.byref(ptr), C.byref(n)))
+    return DeviceWords(ptr.value or 0, n.value, word_length)
+
+
 def count_words(words, word_length: int, n_words: int | None = None) -> Result:
     """Back end of glistmaker for one table of raw words: sort (wordtable_sort, src/word-table.c) and count the
     occurrences of every distinct word (merge_tables_to_file, src/glistmaker.c:1080-1144).  ``words`` is a numpy

@@ -1206,6 +1206,60 @@ int gt4gpu_sequence_words (const void *text, uint64_t n_bytes, uint32_t word_len
   return 0;
 }
 
+int gt4gpu_fasta_words_device (const void *text, uint64_t n_bytes, uint32_t word_length, uint64_t **d_words, uint64_t *n_words)
+{
+  if ((!text && n_bytes) || !d_words || !n_words) return fail (GT4GPU_ERR_ARG, "null argument");
+  if (word_length < 1 || word_length > 32) return fail (GT4GPU_ERR_ARG, "word length %u not in 1..32", word_length);
+  *d_words = nullptr;
+  *n_words = 0;
+  const unsigned char *p = static_cast<const unsigned char *> (text);
+  if (n_bytes == 0 || p[0] == 0) return 0;
+  if (p[0] == '@') return fail (GT4GPU_ERR_ARG, "FastQ images are read on the host (gt4gpu_sequence_words)");
+  if (p[0] != '>') return fail (GT4GPU_ERR_FORMAT, "invalid start tag '%c'", p[0]);          // src/fasta.c:136-139
+  if (const void *z = memchr (p, 0, (size_t) n_bytes)) n_bytes = (uint64_t) (static_cast<const unsigned char *> (z) - p);   // :107-118
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  cudaStream_t st = g_ctx.stream;
+  struct Scratch {
+    void *p[3] = {nullptr, nullptr, nullptr};
+    ~Scratch () { for (void *q : p) dev_free (q); }
+  } tmp;
+  if ((rc = dev_alloc (&tmp.p[0], n_bytes))) return rc;
+  if ((rc = dev_alloc (&tmp.p[1], n_bytes))) return rc;
+  if ((rc = dev_alloc (&tmp.p[2], fasta_scratch_bytes (fasta_chunks (n_bytes))))) return rc;
+  uint8_t *d_text = (uint8_t *) tmp.p[0], *d_codes = (uint8_t *) tmp.p[1];
+  unsigned char *ws = (unsigned char *) tmp.p[2];
+  CU (cudaMemcpyAsync (d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
+  const uint64_t *d_n = nullptr;
+  CU (launch_fasta_codes (d_text, n_bytes, ws, d_codes, &d_n, st));
+  uint64_t n_codes = 0;
+  CU (cudaMemcpyAsync (&n_codes, d_n, sizeof (n_codes), cudaMemcpyDeviceToHost, st));
+  CU (cudaStreamSynchronize (st));
+  if (n_codes > n_bytes) return fail (GT4GPU_ERR_CUDA, "sequence pass kept %llu codes of %llu bytes", (unsigned long long) n_codes, (unsigned long long) n_bytes);
+  CU (launch_fasta_word_counts (d_codes, n_codes, word_length, ws, &d_n, st));
+  uint64_t n = 0;
+  CU (cudaMemcpyAsync (&n, d_n, sizeof (n), cudaMemcpyDeviceToHost, st));
+  CU (cudaStreamSynchronize (st));
+  if (n > n_codes) return fail (GT4GPU_ERR_CUDA, "word pass counted %llu words in %llu codes", (unsigned long long) n, (unsigned long long) n_codes);
+  if (n == 0) return 0;
+  uint64_t *words = nullptr;
+  if ((rc = dev_alloc ((void **) &words, n * sizeof (uint64_t)))) return rc;
+  cudaError_t e = launch_fasta_words (d_codes, n_codes, word_length, ws, words, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize (st);
+  if (e != cudaSuccess) {
+    dev_free (words);
+    return fail (GT4GPU_ERR_CUDA, "word pass: %s", cudaGetErrorString (e));
+  }
+  *d_words = words;
+  *n_words = n;
+  return 0;
+}
+
+void gt4gpu_device_free (void *d_ptr)
+{
+  if (d_ptr && g_ctx.ready) dev_free (d_ptr);
+}
+
 int gt4gpu_count_words (const uint64_t *words, uint64_t n_words, int on_device, uint32_t word_length, gt4gpu_result *out)
 {
   if (!out || (!words && n_words)) return fail (GT4GPU_ERR_ARG, "null argument");

@@ -85,4 +85,14 @@ cudaError_t launch_rle_heads (const uint64_t *sorted, uint64_t n, uint64_t *word
 cudaError_t launch_rle_counts (const uint64_t *words_tmp, const uint64_t *first, uint64_t n_unique, uint64_t n,
                                uint64_t *words, uint32_t *counts, cudaStream_t st);
 
+// ---- FastA text -> canonical words on the device (gt4gpu_fasta_kernel.cu)
+uint64_t fasta_chunks (uint64_t n);
+size_t fasta_scratch_bytes (uint64_t n_chunks);
+cudaError_t launch_fasta_codes (const uint8_t *text, uint64_t n, unsigned char *scratch, uint8_t *codes, const uint64_t **d_n_codes,
+                                cudaStream_t st);
+cudaError_t launch_fasta_word_counts (const uint8_t *codes, uint64_t n_codes, unsigned k, unsigned char *scratch,
+                                      const uint64_t **d_n_words, cudaStream_t st);
+cudaError_t launch_fasta_words (const uint8_t *codes, uint64_t n_codes, unsigned k, const unsigned char *scratch, uint64_t *words,
+                                cudaStream_t st);
+
 }  // namespace gt4gpu

@@ -31,8 +31,11 @@ namespace {
 constexpr int RADIX = 256;
 constexpr int SORT_NT = 512;
 constexpr int SORT_WARPS = SORT_NT / 32;
-constexpr int SORT_ITEMS = 12;
-constexpr int SORT_TILE = SORT_NT * SORT_ITEMS;     // 6144 keys = 48 KiB of shared memory
+#ifndef GT4_SORT_ITEMS
+#define GT4_SORT_ITEMS 16
+#endif
+constexpr int SORT_ITEMS = GT4_SORT_ITEMS;
+constexpr int SORT_TILE = SORT_NT * SORT_ITEMS;     // 8192 keys = 64 KiB of shared memory
 #ifndef GT4_LB_BATCH
 #define GT4_LB_BATCH 4
 #endif
@@ -140,6 +143,9 @@ struct SweepArgs {
   int debug;                            // experiments (GT4GPU_DEBUG): bit 0 = skip the look-back (WRONG output)
 };
 
+#ifndef GT4_SORT_RANK
+#define GT4_SORT_RANK 0     // 0: eight votes per word, 1: shared-memory atomicOr match, 2: match.any
+#endif
 #ifndef GT4_SORT_MIN_CTAS
 #define GT4_SORT_MIN_CTAS 2
 #endif
@@ -149,6 +155,9 @@ radix_onesweep_kernel (const SweepArgs a)
   extern __shared__ __align__ (16) unsigned char smem_raw[];
   uint64_t *s_keys = reinterpret_cast<uint64_t *> (smem_raw);                 // SORT_TILE keys
   __shared__ uint32_t s_whist[SORT_WARPS][RADIX];    // per warp: digit counts, then exclusive prefix over the warps
+#if GT4_SORT_RANK == 1
+  __shared__ uint32_t s_match[SORT_WARPS][RADIX];    // per warp and digit: the lanes that hold it in the current row
+#endif
   __shared__ uint32_t s_dbase[RADIX];                // first slot of every digit inside the regrouped tile
   __shared__ uint64_t s_gbase[RADIX];                // global slot of that first slot, minus s_dbase
   __shared__ uint32_t s_scan[RADIX / 32];
@@ -156,7 +165,12 @@ radix_onesweep_kernel (const SweepArgs a)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd (a.ticket, 1u);   // tiles start in order: a predecessor is always running
-  for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_NT) (&s_whist[0][0])[i] = 0;
+  for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_NT) {
+    (&s_whist[0][0])[i] = 0;
+#if GT4_SORT_RANK == 1
+    (&s_match[0][0])[i] = 0;
+#endif
+  }
   __syncthreads ();
   const uint64_t tile = s_tile;
   const uint64_t base = tile * SORT_TILE;
@@ -175,8 +189,14 @@ radix_onesweep_kernel (const SweepArgs a)
 #pragma unroll
   for (int j = 0; j < SORT_ITEMS; j++) {
     const uint32_t d = (uint32_t) (key[j] >> a.shift) & 255u;
-#ifdef GT4_SORT_MATCH
+#if GT4_SORT_RANK == 2
     const uint32_t peers = __match_any_sync (0xffffffffu, d);
+#elif GT4_SORT_RANK == 1
+    // lanes holding the same digit meet in one shared-memory word: every lane ORs its bit in, then reads the word
+    atomicOr (&s_match[warp][d], 1u << lane);
+    __syncwarp ();
+    const uint32_t peers = s_match[warp][d];
+    __syncwarp ();
 #else
     // lanes holding the same digit, from one ballot per digit bit (match.any is far slower than 8 votes here)
     uint32_t peers = 0xffffffffu;
@@ -192,6 +212,9 @@ radix_onesweep_kernel (const SweepArgs a)
     if (lane == leader) {
       before = s_whist[warp][d];
       s_whist[warp][d] = before + __popc (peers);
+#if GT4_SORT_RANK == 1
+      s_match[warp][d] = 0;
+#endif
     }
     before = __shfl_sync (0xffffffffu, before, leader);
     const uint32_t r = before + __popc (peers & lt_mask);

@@ -199,6 +199,13 @@ int gt4gpu_lookup (const gt4gpu_list *list, const uint64_t *queries, uint64_t n_
  * the words read so far, as glistmaker keeps them.  No device work. */
 int gt4gpu_sequence_words (const void *text, uint64_t n_bytes, uint32_t word_length, uint64_t *words, uint64_t capacity,
                            uint64_t *n_words);
+/* Device form of gt4gpu_sequence_words for FastA images: text is a HOST buffer holding the file image; the canonical
+ * words come back as a library-owned DEVICE array in file order (release it with gt4gpu_device_free), ready for
+ * gt4gpu_count_words (..., on_device = 1, ...).  Same acceptance rules as the host reader; FastQ images return
+ * GT4GPU_ERR_ARG (read them with gt4gpu_sequence_words).  *d_words is NULL when the image holds no k-mer. */
+int gt4gpu_fasta_words_device (const void *text, uint64_t n_bytes, uint32_t word_length, uint64_t **d_words, uint64_t *n_words);
+void gt4gpu_device_free (void *d_ptr);
+
 /* Replaces the back end of glistmaker for one table of raw words: wordtable_sort (src/word-table.c, radix sort of
  * src/utils.c:127-198, called from read_table, src/glistmaker.c:893-968) followed by the run-length counting of
  * merge_tables_to_file (src/glistmaker.c:1080-1144).  words: n_words canonical k-mer words (< 4^word_length) in any

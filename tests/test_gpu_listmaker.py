@@ -5,7 +5,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SORT_TILE = 512 * 12     # keys per CTA of radix_onesweep_kernel
+SORT_TILE = 512 * 16     # keys per CTA of radix_onesweep_kernel
 RLE_TILE = 128 * 16      # keys per CTA of rle_heads_kernel
 
 
@@ -140,3 +140,51 @@ def test_listmaker_cli_against_glistmaker_golden(tmp_path):
     words = np.concatenate([O.sequence_words((gold_dir / f).read_bytes(), 16) for f in ("plain.fa", "multi.fa", "reads.fq")])
     exp = O.count_words(words, 16)
     assert (tmp_path / "all_16.list").read_bytes() == O.header_bytes(16, len(exp.words), int(exp.counts.sum())) + exp.records().tobytes()
+
+
+def test_device_fasta_reader_matches_host_reader(g, oracle):
+    """gt4gpu_fasta_words_device (parallel line-state + compaction kernels) == the byte-serial reader, word for word."""
+    import json
+    from pathlib import Path
+    gold_dir = Path(__file__).parent / "golden" / "maker"
+    texts = [(gold_dir / f).read_bytes() for f in ("plain.fa", "multi.fa", "messy.fa", "repeats.fa", "short.fa")]
+    texts += [b">x", b">x\n", b">x\nACGT", b">x\nAC\nGT\n>y\nTTTT", b">a\nACGTN\x00ACGT", b">a\r\nAC\r\nGT\r\n", b">a\nacgu\n",
+              b">a>b\nAC>GT\nACGT\n", b">\n" + b"ACGT" * 3000 + b"\n", b">n\n" + b"\n" * 5000 + b"ACGTACGT",
+              b">long name " + b"x" * 9000 + b"\nACGTTGCA\n>" + b">" * 5000 + b"\nGGGGCCCC"]
+    rng = np.random.default_rng(21)
+    for _ in range(6):            # random images whose names, lines and N runs straddle the 4 KiB chunks in every way
+        parts = []
+        for r in range(int(rng.integers(1, 60))):
+            name = bytes(rng.choice(list(b"abc >XYZ"), size=int(rng.integers(0, 300))))
+            seq = bytes(rng.choice(list(b"ACGTACGTACGTNacgtn\n\n\r -"), size=int(rng.integers(0, 9000))))
+            parts.append(b">" + name.replace(b"\n", b"") + b"\n" + seq)
+            if rng.random() < 0.2:
+                parts.append(b">inline" * int(rng.integers(1, 4)))
+        texts.append(b"".join(parts))
+    for text in texts:
+        for k in (1, 2, 7, 16, 25, 31, 32):
+            dev = g.fasta_words_device(text, k)
+            host = oracle.sequence_words(text, k)
+            assert dev.n_words == host.size, (text[:60], k)
+            assert np.array_equal(dev.to_host(), host), (text[:60], k)
+            dev.free()
+    for bad, code in ((b"x", 3), (b"ACGT\n", 3), (b"@r\nACGT\n+\nIIII\n", 1)):
+        with pytest.raises(g.GT4GPUError) as e:
+            g.fasta_words_device(bad, 4)
+        assert e.value.code == code
+    assert g.fasta_words_device(b"", 4).n_words == 0
+
+
+def test_device_fasta_to_list_medium(g, oracle):
+    """2 Mbp random genome with N runs: device reader -> count_words (device words) == oracle list."""
+    rng = np.random.default_rng(8)
+    seq = rng.choice(list(b"ACGT"), size=2_000_000).astype(np.uint8)
+    seq[rng.integers(0, seq.size, size=200)] = ord("N")
+    lines = b"\n".join(seq[i:i + 70].tobytes() for i in range(0, seq.size, 70))
+    text = b">chr\n" + lines + b"\n"
+    k = 21
+    dev = g.fasta_words_device(text, k)
+    res = g.count_words(dev.ptr, k, n_words=dev.n_words)
+    exp = oracle.count_words(oracle.sequence_words(text, k), k)
+    w, c = res.to_host()
+    assert np.array_equal(w, exp.words) and np.array_equal(c, exp.counts)
