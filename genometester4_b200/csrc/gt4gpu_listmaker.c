@@ -5,7 +5,8 @@
  * Flag grammar, validation order, messages, the "<out>_<k>.list" name, tmp + rename and exit codes follow main()
  * of /root/reference/src/glistmaker.c:138-366 (help text :1303-1326).  The pipeline mirrors the reference's tasks:
  *
- *   read_table      (:893-968)    sequence file -> a table of canonical words        gt4gpu_sequence_words (host)
+ *   read_table      (:893-968)    sequence file -> a table of canonical words        gt4gpu_fasta_words_device (GPU; FastA)
+ *                                                                                     gt4gpu_sequence_words (host; FastQ)
  *   wordtable_sort + merge_tables_to_file (:924, :1080-1144)   table -> (word, count)  gt4gpu_count_words   (GPU)
  *   collate_files / final gt4_write_union (:787-835, :314-333)  tables -> one list     gt4gpu_union_multi   (GPU)
  *
@@ -69,10 +70,11 @@ static gt4gpu_result tables[4096];
 static gt4gpu_list *table_lists[4096];
 static unsigned n_tables = 0;
 static double t_read = 0, t_sort = 0, t_collate = 0;
+static uint64_t fasta_block = 1ULL << 30;     /* bytes of FastA text parsed per GPU call (GT4GPU_FASTA_BLOCK overrides) */
 static unsigned long long n_read = 0;
 
 static int
-flush_table (uint64_t *words, uint64_t n, unsigned wordlength)
+flush_table (const uint64_t *words, uint64_t n, int on_device, unsigned wordlength)
 {
   double t0 = now ();
   int rc;
@@ -90,7 +92,7 @@ flush_table (uint64_t *words, uint64_t n, unsigned wordlength)
     n_tables = 1;
   }
   memset (&tables[n_tables], 0, sizeof (tables[0]));
-  rc = gt4gpu_count_words (words, n, 0, wordlength, &tables[n_tables]);
+  rc = gt4gpu_count_words (words, n, on_device, wordlength, &tables[n_tables]);
   if (rc) return rc;
   rc = gt4gpu_list_from_device (tables[n_tables].words, tables[n_tables].counts, tables[n_tables].n_words, wordlength, &table_lists[n_tables]);
   if (rc) return rc;
@@ -206,6 +208,8 @@ main (int argc, const char *argv[])
     return 1;
   }
   if (tablesize < 1) tablesize = 1;
+  if (getenv ("GT4GPU_FASTA_BLOCK")) fasta_block = strtoull (getenv ("GT4GPU_FASTA_BLOCK"), NULL, 10);
+  if (fasta_block < 1) fasta_block = 1;
   for (i = 0; i < n_inputs; i++) {
     struct stat s;
     size_t len = strlen (inputs[i]);
@@ -237,6 +241,41 @@ main (int argc, const char *argv[])
       fprintf (stderr, "Cannot map %s\n", inputs[i]);
       return 1;
     }
+    if (text[0] == '>') {
+      /* FastA: parsed on the GPU, block by block (blocks end where a record ends, like the reference's
+       * gt4_sequence_block_split, src/sequence-block.c:149-207); the words never visit the host */
+      const unsigned char *zero = (const unsigned char *) memchr (text, 0, s.st_size);
+      uint64_t size = zero ? (uint64_t) (zero - text) : (uint64_t) s.st_size, off = 0;
+      int rc = 0;
+      while (off < size && !rc) {
+        uint64_t end = size, n_block = 0, taken = 0;
+        uint64_t *d_words = NULL;
+        if (size - off > fasta_block) {
+          const unsigned char *q = text + off + fasta_block;
+          while ((q = (const unsigned char *) memchr (q, '\n', text + size - q)) != NULL) {
+            if (q + 1 < text + size && q[1] == '>') { end = (uint64_t) (q + 1 - text); break; }
+            q++;
+          }
+        }
+        rc = gt4gpu_fasta_words_device (text + off, end - off, wordlength, &d_words, &n_block);
+        t_read += now () - t0;
+        n_read += n_block;
+        while (!rc && taken < n_block) {
+          uint64_t take = n_block - taken < tablesize ? n_block - taken : tablesize;
+          rc = flush_table (d_words + taken, take, 1, wordlength);
+          taken += take;
+        }
+        gt4gpu_device_free (d_words);
+        t0 = now ();
+        off = end;
+      }
+      munmap ((void *) text, s.st_size);
+      if (rc) {
+        fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
+        return 1;
+      }
+      continue;
+    }
     uint64_t *words = (uint64_t *) malloc ((size_t) s.st_size * sizeof (uint64_t) + 8);
     if (!words) {
       fprintf (stderr, "Out of memory reading %s\n", inputs[i]);
@@ -251,7 +290,7 @@ main (int argc, const char *argv[])
       uint64_t take = n_words - done;
       if (table_fill == 0 && take >= tablesize) {
         /* a whole table straight from the reader's buffer */
-        if ((rc = flush_table (words + done, tablesize, wordlength))) goto gpu_error;
+        if ((rc = flush_table (words + done, tablesize, 0, wordlength))) goto gpu_error;
         done += tablesize;
         continue;
       }
@@ -273,7 +312,7 @@ main (int argc, const char *argv[])
       table_fill += take;
       done += take;
       if (table_fill == tablesize) {
-        if ((rc = flush_table (table, table_fill, wordlength))) goto gpu_error;
+        if ((rc = flush_table (table, table_fill, 0, wordlength))) goto gpu_error;
         table_fill = 0;
       }
     }
@@ -284,7 +323,7 @@ gpu_error:
     return 1;
   }
   if (table_fill) {
-    if (flush_table (table, table_fill, wordlength)) {
+    if (flush_table (table, table_fill, 0, wordlength)) {
       fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
       return 1;
     }

@@ -1,5 +1,7 @@
 """GPU parity tests of the list-building back end: gt4gpu_count_words (radix sort +
 run-length counts) through the C ABI against the oracle's restatement of wordtable_sort + merge_tables_to_file."""
+import os
+
 import numpy as np
 import pytest
 
@@ -121,12 +123,14 @@ def test_listmaker_cli_against_glistmaker_golden(tmp_path):
     gold_dir = Path(__file__).parent / "golden" / "maker"
     gold = json.loads((gold_dir / "maker_golden.json").read_text())
     for i, case in enumerate(gold["cases"]):
-        if i % 2 and case["k"] not in (1, 32):
+        if i % 3 == 2 and case["k"] not in (1, 32):
             continue
         # "--table_size N" swallows the token after N as well (src/glistmaker.c:214), hence the filler
         extra = [[], ["--table_size", "1000", "filler"], ["--table_size", "37", "filler", "-D"]][i % 3]
+        # FastA text goes to the GPU reader in blocks that end where a record ends: tiny blocks exercise the splitting
+        env = {**os.environ, "GT4GPU_FASTA_BLOCK": "700"} if i % 4 == 1 else None
         r = subprocess.run([str(_lib.listmaker_cli_path()), str(gold_dir / case["input"]), "-w", str(case["k"]), "-o", "t", *extra],
-                           cwd=tmp_path, capture_output=True)
+                           cwd=tmp_path, capture_output=True, env=env)
         assert r.returncode == 0, (case, r.stderr)
         data = (tmp_path / f"t_{case['k']}.list").read_bytes()
         assert len(data) == case["bytes"] and hashlib.sha256(data).hexdigest() == case["sha256"], (case, extra)
