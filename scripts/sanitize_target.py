@@ -21,4 +21,21 @@ g.compare_wordmaps(la, lb, find_union=1, find_intrsec=1, find_diff=1, find_ddiff
 g.set_option("use_stream_kernel", 1)
 lists = [g.WordList.from_arrays(*synth.list_numpy(5, 25, 30_000, 0, 30_000, j, 0.4), 25) for j in range(5)]
 g.union_multi(lists, cutoff=2).records(); g.intersect_multi(lists).records(); g.gt4_union(lists); g.gt4_is_union(lists)
+# list building, device FastA reader, lookups
+rng = np.random.default_rng(2)
+for k, n in ((5, 1), (16, 8191), (25, 8193), (32, 40_000)):
+    hi = min(4 ** k, 2 ** 63)
+    raw = rng.integers(0, hi, size=n, dtype=np.uint64)
+    res = g.count_words(raw, k)
+    w, c = res.to_host()
+    assert int(c.sum()) == n
+    lst = g.WordList.from_arrays(w, c, k)
+    g.lookup(lst, rng.integers(0, hi, size=3001, dtype=np.uint64))
+for text in (b">a\nACGT", b">x\n" + bytes(rng.choice(list(b"ACGTN\n"), size=20_001)) + b"\n>y z\n" + bytes(rng.choice(list(b"ACGT"), size=4095)),
+             b">" + b"n" * 5000 + b"\n" + b"ACGT" * 2500):
+    for k in (1, 13, 32):
+        d = g.fasta_words_device(text, k)
+        if d.n_words:
+            g.count_words(d.ptr, k, n_words=d.n_words).to_host()
+        d.free()
 print("sanitize target ok")
