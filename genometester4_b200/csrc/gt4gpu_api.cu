@@ -1073,6 +1073,49 @@ int gt4gpu_union_matrix (const gt4gpu_list *const *lists, unsigned n_lists, int 
 
 // ------------------------------------------------------------------ lookups
 
+// Device-side body of gt4gpu_lookup.  Large batches are sorted first (key-value radix sort of the canonical words with
+// their positions): neighbouring threads then share their search paths and the probes hit cache instead of DRAM.
+static int lookup_on_device (const gt4gpu_list *list, const uint64_t *d_queries, uint64_t n, int canonize, uint32_t *d_counts,
+                             uint64_t *d_canonical)
+{
+  cudaStream_t st = g_ctx.stream;
+  const char *env = getenv ("GT4GPU_LOOKUP_SORT_MIN");
+  const uint64_t sort_min = env ? strtoull (env, nullptr, 10) : (1ull << 20);
+  if (n < sort_min || n > 0xffffffffull || list->n_words < 2) {
+    CU (launch_lookup (list->words, list->counts, list->n_words, list->word_length, canonize, d_queries, n, d_canonical, d_counts, st));
+    return 0;
+  }
+  struct Scratch {
+    void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Scratch () { for (void *q : p) dev_free (q); }
+  } tmp;
+  int rc;
+  if ((rc = dev_alloc (&tmp.p[0], n * sizeof (uint64_t)))) return rc;
+  if ((rc = dev_alloc (&tmp.p[1], n * sizeof (uint64_t)))) return rc;
+  if ((rc = dev_alloc (&tmp.p[2], n * sizeof (uint32_t)))) return rc;
+  if ((rc = dev_alloc (&tmp.p[3], n * sizeof (uint32_t)))) return rc;
+  if ((rc = dev_alloc (&tmp.p[4], sort_scratch_bytes (n)))) return rc;
+  uint64_t *keys = (uint64_t *) tmp.p[0], *alt = (uint64_t *) tmp.p[1];
+  CU (launch_canonize (d_queries, n, list->word_length, canonize, keys, st));
+  if (d_canonical) CU (cudaMemcpyAsync (d_canonical, keys, n * sizeof (uint64_t), cudaMemcpyDeviceToDevice, st));
+  // a batch that arrives in order (a list's own words, a sorted query file) needs no sorting
+  uint32_t unsorted = 1;
+  CU (launch_check_sorted (keys, n, (uint32_t *) tmp.p[2], st));
+  CU (cudaMemcpyAsync (&unsorted, tmp.p[2], sizeof (unsorted), cudaMemcpyDeviceToHost, st));
+  CU (cudaStreamSynchronize (st));
+  if (!unsorted) {
+    CU (launch_lookup (list->words, list->counts, list->n_words, list->word_length, 0, keys, n, nullptr, d_counts, st));
+    return 0;
+  }
+  const int n_pass = (int) ((2 * list->word_length + 7) / 8);
+  uint64_t *sorted = nullptr;
+  uint32_t *perm = nullptr;
+  CU (launch_radix_sort_pairs (keys, alt, (uint32_t *) tmp.p[2], (uint32_t *) tmp.p[3], n, n_pass, (unsigned char *) tmp.p[4],
+                               g_ctx.sm_count, &sorted, &perm, st));
+  CU (launch_lookup_sorted (list->words, list->counts, list->n_words, sorted, perm, n, d_counts, st));
+  return 0;
+}
+
 int gt4gpu_lookup (const gt4gpu_list *list, const uint64_t *queries, uint64_t n_queries, int on_device, int canonize,
                    uint32_t *counts_out, uint64_t *canonical_out)
 {
@@ -1082,7 +1125,7 @@ int gt4gpu_lookup (const gt4gpu_list *list, const uint64_t *queries, uint64_t n_
   if (n_queries == 0) return 0;
   cudaStream_t st = g_ctx.stream;
   if (on_device) {
-    CU (launch_lookup (list->words, list->counts, list->n_words, list->word_length, canonize, queries, n_queries, canonical_out, counts_out, st));
+    if ((rc = lookup_on_device (list, queries, n_queries, canonize, counts_out, canonical_out))) return rc;
     CU (cudaStreamSynchronize (st));
     return 0;
   }
@@ -1094,8 +1137,7 @@ int gt4gpu_lookup (const gt4gpu_list *list, const uint64_t *queries, uint64_t n_
   if ((rc = dev_alloc (&tmp.p[1], n_queries * sizeof (uint32_t)))) return rc;
   if (canonical_out && (rc = dev_alloc (&tmp.p[2], n_queries * sizeof (uint64_t)))) return rc;
   CU (cudaMemcpyAsync (tmp.p[0], queries, n_queries * sizeof (uint64_t), cudaMemcpyHostToDevice, st));
-  CU (launch_lookup (list->words, list->counts, list->n_words, list->word_length, canonize, (const uint64_t *) tmp.p[0], n_queries,
-                     (uint64_t *) tmp.p[2], (uint32_t *) tmp.p[1], st));
+  if ((rc = lookup_on_device (list, (const uint64_t *) tmp.p[0], n_queries, canonize, (uint32_t *) tmp.p[1], (uint64_t *) tmp.p[2]))) return rc;
   CU (cudaMemcpyAsync (counts_out, tmp.p[1], n_queries * sizeof (uint32_t), cudaMemcpyDeviceToHost, st));
   if (canonical_out) CU (cudaMemcpyAsync (canonical_out, tmp.p[2], n_queries * sizeof (uint64_t), cudaMemcpyDeviceToHost, st));
   CU (cudaStreamSynchronize (st));

@@ -72,6 +72,11 @@ cudaError_t launch_scatter_counts (const uint64_t *rows, uint64_t n_rows, const 
 // counts_out[i] = count of queries[i] (canonical form when canonize) in the list, 0 when absent
 cudaError_t launch_lookup (const uint64_t *words, const uint32_t *counts, uint64_t n, unsigned k, int canonize,
                            const uint64_t *queries, uint64_t n_queries, uint64_t *canonical_out, uint32_t *counts_out, cudaStream_t st);
+// the sorted-batch route: canonical form of every query; then, on the sorted queries, counts_out[perm[i]] = count of sorted[i]
+cudaError_t launch_canonize (const uint64_t *queries, uint64_t n_queries, unsigned k, int canonize, uint64_t *canonical, cudaStream_t st);
+cudaError_t launch_check_sorted (const uint64_t *keys, uint64_t n, uint32_t *unsorted, cudaStream_t st);
+cudaError_t launch_lookup_sorted (const uint64_t *words, const uint32_t *counts, uint64_t n, const uint64_t *sorted_queries,
+                                  const uint32_t *perm, uint64_t n_queries, uint32_t *counts_out, cudaStream_t st);
 
 // ---- list building (gt4gpu_sort_kernel.cu): least-significant-digit radix sort of raw words + run-length counts
 static constexpr int SORT_MAX_PASSES = 8;                                        // 8-bit digits of a 64-bit word
@@ -79,6 +84,9 @@ static constexpr size_t SORT_SCRATCH_HEAD = 2 * SORT_MAX_PASSES * 256 * 8 + 256;
 size_t sort_scratch_bytes (uint64_t n);
 cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch, int sm_count,
                                uint64_t **sorted, cudaStream_t st);
+// same with a 32-bit payload per key; the first pass fills it with the key's index, so *sorted_vals is the sorting permutation
+cudaError_t launch_radix_sort_pairs (uint64_t *keys, uint64_t *alt, uint32_t *vals, uint32_t *valt, uint64_t n, int n_pass,
+                                     unsigned char *scratch, int sm_count, uint64_t **sorted, uint32_t **sorted_vals, cudaStream_t st);
 size_t rle_scratch_bytes (uint64_t n);
 cudaError_t launch_rle_heads (const uint64_t *sorted, uint64_t n, uint64_t *words_tmp, uint64_t *first, unsigned char *scratch,
                               int sm_count, unsigned long long **d_n_unique, cudaStream_t st);

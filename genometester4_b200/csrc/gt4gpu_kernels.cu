@@ -521,6 +521,71 @@ lookup_kernel (const uint64_t *__restrict__ words, const uint32_t *__restrict__ 
   counts_out[q] = c;
 }
 
+__global__ void __launch_bounds__ (256)
+canonize_kernel (const uint64_t *__restrict__ queries, uint64_t n_queries, unsigned k, int canonize, uint64_t *__restrict__ canonical)
+{
+  const uint64_t q = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  uint64_t w = queries[q];
+  if (canonize) {
+    const uint64_t r = reverse_complement (w, k);
+    if (r < w) w = r;
+  }
+  canonical[q] = w;
+}
+
+// queries in ascending order: neighbouring threads walk the same search path, so all but the last few probes hit L1 / L2
+__global__ void __launch_bounds__ (256)
+lookup_sorted_kernel (const uint64_t *__restrict__ words, const uint32_t *__restrict__ counts, uint64_t n,
+                      const uint64_t *__restrict__ sorted_queries, const uint32_t *__restrict__ perm, uint64_t n_queries,
+                      uint32_t *__restrict__ counts_out)
+{
+  const uint64_t q = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  const uint64_t w = sorted_queries[q];
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg (words + mid) < w) lo = mid + 1;
+    else hi = mid;
+  }
+  uint32_t c = 0;
+  if (lo < n && __ldg (words + lo) == w) c = __ldg (counts + lo);
+  counts_out[perm[q]] = c;
+}
+
+// *unsorted |= 1 when some element is smaller than its predecessor
+__global__ void __launch_bounds__ (256)
+check_sorted_kernel (const uint64_t *__restrict__ keys, uint64_t n, uint32_t *unsorted)
+{
+  const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const bool bad = i + 1 < n && keys[i] > keys[i + 1];
+  if (__syncthreads_or (bad) && threadIdx.x == 0) atomicOr (unsorted, 1u);
+}
+
+cudaError_t launch_check_sorted (const uint64_t *keys, uint64_t n, uint32_t *unsorted, cudaStream_t st)
+{
+  cudaError_t e = cudaMemsetAsync (unsorted, 0, sizeof (uint32_t), st);
+  if (e != cudaSuccess || n < 2) return e;
+  check_sorted_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>> (keys, n, unsorted);
+  return cudaGetLastError ();
+}
+
+cudaError_t launch_canonize (const uint64_t *queries, uint64_t n_queries, unsigned k, int canonize, uint64_t *canonical, cudaStream_t st)
+{
+  if (n_queries == 0) return cudaSuccess;
+  canonize_kernel<<<(unsigned) ((n_queries + 255) / 256), 256, 0, st>>> (queries, n_queries, k, canonize, canonical);
+  return cudaGetLastError ();
+}
+
+cudaError_t launch_lookup_sorted (const uint64_t *words, const uint32_t *counts, uint64_t n, const uint64_t *sorted_queries,
+                                  const uint32_t *perm, uint64_t n_queries, uint32_t *counts_out, cudaStream_t st)
+{
+  if (n_queries == 0) return cudaSuccess;
+  lookup_sorted_kernel<<<(unsigned) ((n_queries + 255) / 256), 256, 0, st>>> (words, counts, n, sorted_queries, perm, n_queries, counts_out);
+  return cudaGetLastError ();
+}
+
 cudaError_t launch_lookup (const uint64_t *words, const uint32_t *counts, uint64_t n, unsigned k, int canonize,
                            const uint64_t *queries, uint64_t n_queries, uint64_t *canonical_out, uint32_t *counts_out, cudaStream_t st)
 {

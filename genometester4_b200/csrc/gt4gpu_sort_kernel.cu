@@ -140,6 +140,8 @@ struct SweepArgs {
   const unsigned long long *bins;       // [RADIX] of this pass
   uint64_t *desc;                       // [n_tiles][RADIX]
   uint32_t *ticket;                     // one per pass, zeroed
+  const uint32_t *vin;                  // key-value passes: payload of every key (NULL in the first pass: the key's index)
+  uint32_t *vout;
   int debug;                            // experiments (GT4GPU_DEBUG): bit 0 = skip the look-back (WRONG output)
 };
 
@@ -149,6 +151,7 @@ struct SweepArgs {
 #ifndef GT4_SORT_MIN_CTAS
 #define GT4_SORT_MIN_CTAS 2
 #endif
+template <bool VALUES>
 __global__ void __launch_bounds__ (SORT_NT, GT4_SORT_MIN_CTAS)
 radix_onesweep_kernel (const SweepArgs a)
 {
@@ -162,6 +165,7 @@ radix_onesweep_kernel (const SweepArgs a)
   __shared__ uint64_t s_gbase[RADIX];                // global slot of that first slot, minus s_dbase
   __shared__ uint32_t s_scan[RADIX / 32];
   __shared__ uint32_t s_tile;
+  __shared__ uint8_t s_digit[VALUES ? SORT_TILE : 1];   // key-value passes: digit of every regrouped slot
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd (a.ticket, 1u);   // tiles start in order: a predecessor is always running
@@ -184,6 +188,14 @@ radix_onesweep_kernel (const SweepArgs a)
   for (int j = 0; j < SORT_ITEMS; j++) {
     const int idx = warp * 32 * SORT_ITEMS + j * 32 + lane;
     key[j] = idx < n_valid ? a.in[base + idx] : ~0ull;     // padding sorts behind every real key of the tile
+  }
+  uint32_t val[VALUES ? SORT_ITEMS : 1];
+  if (VALUES) {
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+      const int idx = warp * 32 * SORT_ITEMS + j * 32 + lane;
+      val[j] = idx < n_valid ? (a.vin ? a.vin[base + idx] : (uint32_t) (base + idx)) : 0u;
+    }
   }
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -298,6 +310,24 @@ radix_onesweep_kernel (const SweepArgs a)
       const uint64_t k = s_keys[idx];
       const uint32_t d = (uint32_t) (k >> a.shift) & 255u;
       a.out[s_gbase[d] + idx] = k;
+      if (VALUES) s_digit[idx] = (uint8_t) d;
+    }
+  }
+  if (VALUES) {
+    // the payloads take the same route through the (now free) staging buffer
+    uint32_t *s_vals = reinterpret_cast<uint32_t *> (smem_raw);
+    __syncthreads ();
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+      const uint32_t d = (uint32_t) (key[j] >> a.shift) & 255u;
+      const uint32_t r = (j & 1) ? rank2[j / 2] >> 16 : rank2[j / 2] & 0xffffu;
+      s_vals[s_dbase[d] + s_whist[warp][d] + r] = val[j];
+    }
+    __syncthreads ();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+      const int idx = tid + i * SORT_NT;
+      if (idx < n_valid) a.vout[s_gbase[s_digit[idx]] + idx] = s_vals[idx];
     }
   }
 }
@@ -463,12 +493,15 @@ size_t sort_scratch_bytes (uint64_t n)
 
 // Sorts n keys ascending on their low 8 * n_pass bits.  `keys` and `alt` are both n entries; the result lands in
 // keys when n_pass is even, in alt when odd (returned through *sorted).  scratch: sort_scratch_bytes (n), any content.
-cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch, int sm_count,
-                               uint64_t **sorted, cudaStream_t st)
+// With vals / valt (n u32 each) every key drags a payload along: vals is filled by the first pass with the key's
+// original index, *sorted_vals is the permutation that sorts the input.
+static cudaError_t radix_sort_impl (uint64_t *keys, uint64_t *alt, uint32_t *vals, uint32_t *valt, uint64_t n, int n_pass,
+                                    unsigned char *scratch, int sm_count, uint64_t **sorted, uint32_t **sorted_vals, cudaStream_t st)
 {
   *sorted = keys;
-  if (n == 0 || n_pass == 0) return cudaSuccess;
-  if (n_pass > SORT_MAX_PASSES) return cudaErrorInvalidValue;
+  if (sorted_vals) *sorted_vals = vals;
+  if (n == 0) return cudaSuccess;
+  if (n_pass > SORT_MAX_PASSES || n_pass < 1) return cudaErrorInvalidValue;
   const uint64_t n_tiles = (n + SORT_TILE - 1) / SORT_TILE;
   if (n_tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   // scratch head: hist [8][256] u64 | bins [8][256] u64 | tickets [8] u32
@@ -487,11 +520,14 @@ cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_
   static bool configured = false;   // benign race: the attribute is idempotent
   const size_t smem = (size_t) SORT_TILE * sizeof (uint64_t);
   if (!configured) {
-    e = cudaFuncSetAttribute (radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    e = cudaFuncSetAttribute (radix_onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute (radix_onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   uint64_t *src = keys, *dst = alt;
+  uint32_t *vsrc = nullptr, *vdst = vals;      // the first pass writes the identity permutation's image into vals
   for (int p = 0; p < n_pass; p++) {
     SweepArgs a;
     a.in = src; a.out = dst; a.n = n; a.n_tiles = n_tiles;
@@ -500,12 +536,33 @@ cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_
     a.bins = bins + p * RADIX;
     a.desc = desc;
     a.ticket = tickets + p;
+    a.vin = vsrc; a.vout = vdst;
     a.debug = getenv ("GT4GPU_DEBUG") ? atoi (getenv ("GT4GPU_DEBUG")) : 0;
-    radix_onesweep_kernel<<<(unsigned) n_tiles, SORT_NT, smem, st>>> (a);
+    if (vals) radix_onesweep_kernel<true><<<(unsigned) n_tiles, SORT_NT, smem, st>>> (a);
+    else radix_onesweep_kernel<false><<<(unsigned) n_tiles, SORT_NT, smem, st>>> (a);
     uint64_t *t = src; src = dst; dst = t;
+    if (vals) {
+      vsrc = vdst;
+      vdst = (vdst == vals) ? valt : vals;
+    }
   }
   *sorted = src;
+  if (sorted_vals) *sorted_vals = vsrc;
   return cudaGetLastError ();
+}
+
+cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch, int sm_count,
+                               uint64_t **sorted, cudaStream_t st)
+{
+  if (n_pass == 0) { *sorted = keys; return cudaSuccess; }
+  return radix_sort_impl (keys, alt, nullptr, nullptr, n, n_pass, scratch, sm_count, sorted, nullptr, st);
+}
+
+cudaError_t launch_radix_sort_pairs (uint64_t *keys, uint64_t *alt, uint32_t *vals, uint32_t *valt, uint64_t n, int n_pass,
+                                     unsigned char *scratch, int sm_count, uint64_t **sorted, uint32_t **sorted_vals, cudaStream_t st)
+{
+  if (n > 0xffffffffull) return cudaErrorInvalidValue;     // payloads are 32-bit indices
+  return radix_sort_impl (keys, alt, vals, valt, n, n_pass, scratch, sm_count, sorted, sorted_vals, st);
 }
 
 size_t rle_scratch_bytes (uint64_t n)

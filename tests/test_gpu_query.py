@@ -52,6 +52,27 @@ def test_lookup_random_vs_oracle(k, n, nq, g, oracle):
     assert (cc > 0).sum() >= nq // 2
 
 
+def test_lookup_sorted_route_equals_direct_route(g, oracle, monkeypatch):
+    """Large batches are sorted first (key-value radix sort) and scattered back; both routes must agree with the oracle."""
+    k = 13
+    rng = np.random.default_rng(44)
+    words = np.unique(rng.integers(0, 4 ** k, size=400_000, dtype=np.uint64))
+    counts = rng.integers(1, 1000, size=words.size).astype(np.uint32)
+    gl = g.WordList.from_arrays(words, counts, k)
+    lst = oracle.SList(words, counts, k)
+    for nq in (1, 8191, 8193, 70_001):
+        q = rng.integers(0, 4 ** k, size=nq, dtype=np.uint64)
+        ow, oc = oracle.lookup(lst, q)
+        for sort_min in ("1", "1000000000"):
+            monkeypatch.setenv("GT4GPU_LOOKUP_SORT_MIN", sort_min)
+            cw, cc = g.lookup(gl, q)
+            assert np.array_equal(cw, ow) and np.array_equal(cc, oc), (nq, sort_min)
+            # a batch whose canonical words are already ascending skips the sort
+            cw2, cc2 = g.lookup(gl, np.sort(ow), canonize=False)
+            i = np.argsort(ow, kind="stable")
+            assert np.array_equal(cw2, ow[i]) and np.array_equal(cc2, oc[i])
+
+
 def test_lookup_edges(g, oracle):
     empty = g.WordList.from_arrays(np.zeros(0, np.uint64), np.zeros(0, np.uint32), 16)
     cw, cc = g.lookup(empty, np.array([0, 5, 2 ** 32 - 1], dtype=np.uint64))
