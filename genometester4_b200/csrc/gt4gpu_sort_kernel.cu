@@ -214,9 +214,17 @@ radix_onesweep_kernel (const SweepArgs a)
     uint32_t peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < 8; b++) {
+#ifdef GT4_SORT_VOTE_SELECT
       const bool bit = (d >> b) & 1u;
       const uint32_t vote = __ballot_sync (0xffffffffu, bit);
       peers &= bit ? vote : ~vote;
+#else
+      // all-ones when the bit is set (signed 1-bit field extract), so peers &= ~(vote ^ ones) is a single LOP3
+      int ones;
+      asm ("bfe.s32 %0, %1, %2, 1;" : "=r"(ones) : "r"(d), "r"(b));
+      const uint32_t vote = __ballot_sync (0xffffffffu, ones != 0);
+      peers &= ~(vote ^ (uint32_t) ones);
+#endif
     }
 #endif
     const int leader = __ffs (peers) - 1;
