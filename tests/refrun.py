@@ -3,6 +3,7 @@ and build the exact bytes each output file must have."""
 from __future__ import annotations
 
 import hashlib
+import subprocess
 from pathlib import Path
 
 from oracle import oracle as O
@@ -111,6 +112,9 @@ def build_config1_lists(tmp: Path):
     out = []
     for name, s in (("g1", g1), ("g2", g2)):
         (tmp / f"{name}.fa").write_text(f">{name}\n" + "\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n")
-        O.run_ref("glistmaker", [f"{name}.fa", "-w", "16", "-o", name], cwd=tmp, check=True)
+        try:
+            O.run_ref("glistmaker", [f"{name}.fa", "-w", "16", "-o", name], cwd=tmp, check=True)
+        except subprocess.TimeoutExpired:      # the reference's own shutdown race (see oracle.run_ref): no lists, callers skip
+            return None
         out.append(tmp / f"{name}_16.list")
     return out
