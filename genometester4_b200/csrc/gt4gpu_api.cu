@@ -37,6 +37,21 @@ struct gt4gpu_list {
   int owned;
 };
 
+namespace gt4gpu {
+
+int debug_flags ()
+{
+  const char *env = getenv ("GT4GPU_DEBUG");
+  if (!env) return 0;
+#ifdef GT4GPU_UNSAFE_EXPERIMENTS
+  return atoi (env);
+#else
+  return atoi (env) & (2 | 4 | 32);
+#endif
+}
+
+}  // namespace gt4gpu
+
 namespace {
 
 constexpr uint32_t LIST_CODE = (uint32_t) ('G' << 24 | 'T' << 16 | '4' << 8 | 'C');   // src/word-list.c:31
@@ -178,7 +193,7 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   args.p = p;
   args.p.ops = stream_mask;
   args.stream0 = __builtin_ctz (stream_mask);
-  args.debug = getenv ("GT4GPU_DEBUG") ? atoi (getenv ("GT4GPU_DEBUG")) : 0;
+  args.debug = debug_flags ();
   for (int s = 0; s < 4; s++) {
     args.out_words[s] = out[s].words;
     args.out_counts[s] = out[s].counts;

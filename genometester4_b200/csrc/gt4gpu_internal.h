@@ -9,6 +9,12 @@
 
 namespace gt4gpu {
 
+// Experiment switches (environment GT4GPU_DEBUG, a bit mask).  Measurement-only bits are always honoured: 2 = look-back
+// statistics, 4 = no L2 prefetch, 32 = per-phase cycle counters of the merge consumers.  Bits that change what a kernel
+// computes (1 / 8 / 16: skip a look-back or the stores -- WRONG output, timing experiments only) are ignored unless the
+// library is built with -DGT4GPU_UNSAFE_EXPERIMENTS.
+int debug_flags ();
+
 // Per-call scratch living in HBM, zeroed before every launch.
 //   [0]      u32 ticket       -- dynamic tile counter (tiles are claimed in launch order so the
 //                                decoupled look-back never waits on a tile that has not started)

@@ -15,65 +15,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gt4gpu_device.cuh"
 #include "gt4gpu_internal.h"
 
 namespace gt4gpu {
 
-// ------------------------------------------------------------------------------------------
-// look-back descriptors: one u64 per (stream, tile): status in the top 2 bits, value below.
-// A single relaxed 64-bit store publishes status and value together, so no fence is needed.
-// ------------------------------------------------------------------------------------------
-static constexpr uint64_t DESC_PARTIAL = 1ull << 62;     // value = this tile's own count
-static constexpr uint64_t DESC_INCLUSIVE = 2ull << 62;   // value = inclusive prefix up to this tile
-static constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1;
-
-__device__ __forceinline__ uint64_t ld_relaxed (const uint64_t *p)
-{
-  uint64_t v;
-  asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void st_relaxed (uint64_t *p, uint64_t v)
-{
-  asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ uint64_t warp_sum_u64 (uint64_t v)
-{
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync (0xffffffffu, v, off);
-  return v;
-}
-
-// Executed by all 32 lanes of warp 0.  Returns the exclusive prefix of `aggregate` over tiles.
-__device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t tile, uint64_t aggregate, int lane)
-{
-  if (tile == 0) {
-    if (lane == 0) st_relaxed (desc, DESC_INCLUSIVE | aggregate);
-    return 0;
-  }
-  if (lane == 0) st_relaxed (desc + tile, DESC_PARTIAL | aggregate);
-  uint64_t exclusive = 0;
-  int64_t pred = (int64_t) tile - 1;     // lane l inspects tile pred - l
-  while (true) {
-    const int64_t idx = pred - lane;
-    uint64_t d = (idx >= 0) ? ld_relaxed (desc + idx) : DESC_INCLUSIVE;
-    while (__any_sync (0xffffffffu, (d >> 62) == 0)) {
-      if ((d >> 62) == 0) d = ld_relaxed (desc + idx);
-    }
-    const uint32_t incl = __ballot_sync (0xffffffffu, (d >> 62) == 2);
-    if (incl) {
-      const int first = __ffs (incl) - 1;   // nearest predecessor that already knows its prefix
-      exclusive += warp_sum_u64 (lane <= first ? (d & DESC_VALUE_MASK) : 0ull);
-      break;
-    }
-    exclusive += warp_sum_u64 (d & DESC_VALUE_MASK);
-    pred -= 32;
-  }
-  if (lane == 0) st_relaxed (desc + tile, DESC_INCLUSIVE | (exclusive + aggregate));
-  return exclusive;
-}
+using namespace dev;
 
 // ------------------------------------------------------------------------------------------
 // partition
@@ -294,7 +241,7 @@ setop2_tile_kernel (const TileArgs args)
     if (!COUNT_ONLY) {
       // warp 0 resolves the global offset while the other warps already compact
       if (warp == 0) {
-        const uint64_t base = lookback_exclusive (args.desc + (uint64_t) q * args.n_tiles, tile, (uint64_t) tile_cnt, lane);
+        const uint64_t base = lookback_exclusive<1> (args.desc + (uint64_t) q * args.n_tiles, tile, (uint64_t) tile_cnt, lane);
         if (lane == 0) s_base = base;
       }
       int pos = excl;

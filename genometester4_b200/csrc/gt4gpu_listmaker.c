@@ -114,72 +114,63 @@ main (int argc, const char *argv[])
   int create_index = 0;
   char tmp_name[1024], out_name[1024];
 
+  /* integer options: names, what the complaint calls them, where the value goes */
+  long long v_word = 0, v_min = DEFAULT_CUTOFF, v_max = 0xffffffffLL, v_threads = DEFAULT_NUM_THREADS, v_tables = DEFAULT_NUM_TABLES,
+            v_tsize = (long long) DEFAULT_TABLE_WORDS;
+  const struct {
+    const char *name[3];
+    const char *what;
+    long long *value;
+    int swallow_next;      /* --table_size also skips the token after its value (src/glistmaker.c:214) */
+  } int_opts[] = {
+    {{"-w", "--wordlength", NULL}, "word-length", &v_word, 0},
+    {{"-c", "--cutoff", "--min"}, "frequency cut-off", &v_min, 0},
+    {{"--max", NULL, NULL}, "frequency cut-off", &v_max, 0},
+    {{"--num_threads", NULL, NULL}, "num-threads", &v_threads, 0},
+    {{"--max_tables", NULL, NULL}, "max_tables", &v_tables, 0},
+    {{"--table_size", NULL, NULL}, "table-size", &v_tsize, 1},
+  };
   for (i = 1; i < (unsigned int) argc; i++) {
-    if (!strcmp (argv[i], "-v") || !strcmp (argv[i], "--version")) {
+    const char *a = argv[i];
+    unsigned int o, m, hit = 0;
+    for (o = 0; o < sizeof (int_opts) / sizeof (int_opts[0]) && !hit; o++) {
+      for (m = 0; m < 3 && int_opts[o].name[m]; m++) {
+        if (strcmp (a, int_opts[o].name[m])) continue;
+        if (++i >= (unsigned int) argc) print_help (1);
+        *int_opts[o].value = strtoll (argv[i], &end, 10);
+        if (*end != 0) {
+          fprintf (stderr, "Error: Invalid %s: %s! Must be an integer.\n", int_opts[o].what, argv[i]);
+          print_help (1);
+        }
+        i += int_opts[o].swallow_next;
+        hit = 1;
+        break;
+      }
+    }
+    if (hit) continue;
+    if (!strcmp (a, "-v") || !strcmp (a, "--version")) {
       fprintf (stdout, "glistmaker version %u.%u.%u (%s)\n", GT4GPU_VERSION_MAJOR, GT4GPU_VERSION_MINOR, GT4GPU_VERSION_MICRO, "stable");
       return 0;
-    } else if (!strcmp (argv[i], "-h") || !strcmp (argv[i], "--help") || !strcmp (argv[i], "-?")) {
-      print_help (0);
-    } else if (!strcmp (argv[i], "-o") || !strcmp (argv[i], "--outputname")) {
-      if (++i >= (unsigned int) argc) print_help (1);
-      outputname = argv[i];
-    } else if (!strcmp (argv[i], "-w") || !strcmp (argv[i], "--wordlength")) {
-      if (++i >= (unsigned int) argc) print_help (1);
-      wordlength = strtol (argv[i], &end, 10);
-      if (*end != 0) {
-        fprintf (stderr, "Error: Invalid word-length: %s! Must be an integer.\n", argv[i]);
-        print_help (1);
-      }
-    } else if (!strcmp (argv[i], "-c") || !strcmp (argv[i], "--cutoff") || !strcmp (argv[i], "--min")) {
-      if (++i >= (unsigned int) argc) print_help (1);
-      min = strtol (argv[i], &end, 10);
-      if (*end != 0) {
-        fprintf (stderr, "Error: Invalid frequency cut-off: %s! Must be an integer.\n", argv[i]);
-        print_help (1);
-      }
-    } else if (!strcmp (argv[i], "--max")) {
-      if (++i >= (unsigned int) argc) print_help (1);
-      max = strtol (argv[i], &end, 10);
-      if (*end != 0) {
-        fprintf (stderr, "Error: Invalid frequency cut-off: %s! Must be an integer.\n", argv[i]);
-        print_help (1);
-      }
-    } else if (!strcmp (argv[i], "--num_threads")) {
-      if (++i >= (unsigned int) argc) print_help (1);
-      nthreads = strtol (argv[i], &end, 10);
-      if (*end != 0) {
-        fprintf (stderr, "Error: Invalid num-threads: %s! Must be an integer.\n", argv[i]);
-        print_help (1);
-      }
-    } else if (!strcmp (argv[i], "--max_tables")) {
-      if (++i >= (unsigned int) argc) print_help (1);
-      ntables = strtol (argv[i], &end, 10);
-      if (*end != 0) {
-        fprintf (stderr, "Error: Invalid max_tables: %s! Must be an integer.\n", argv[i]);
-        print_help (1);
-      }
-    } else if (!strcmp (argv[i], "--table_size")) {
-      if (++i >= (unsigned int) argc) print_help (1);
-      tablesize = strtoll (argv[i], &end, 10);
-      if (*end != 0) {
-        fprintf (stderr, "Error: Invalid table-size: %s! Must be an integer.\n", argv[i]);
-        print_help (1);
-      }
-      i += 1;     /* the reference skips the token after the value too (:214) */
-    } else if (!strcmp (argv[i], "--tmpdir")) {
-      if (++i >= (unsigned int) argc) print_help (1);
-    } else if (!strcmp (argv[i], "--stream")) {
-      /* nothing to choose: inputs are mapped and parsed in one go */
-    } else if (!strcmp (argv[i], "--index")) {
-      create_index = 1;
-    } else if (!strcmp (argv[i], "-D")) {
-      debug += 1;
-    } else {
-      if ((argv[i][0] == '-') && argv[i][1]) print_help (1);
-      if (n_inputs >= MAX_INPUTS) continue;
-      inputs[n_inputs++] = argv[i];
     }
+    if (!strcmp (a, "-h") || !strcmp (a, "--help") || !strcmp (a, "-?")) print_help (0);
+    if (!strcmp (a, "-o") || !strcmp (a, "--outputname") || !strcmp (a, "--tmpdir")) {
+      if (++i >= (unsigned int) argc) print_help (1);
+      if (strcmp (a, "--tmpdir")) outputname = argv[i];          /* --tmpdir: accepted, no temporary files here */
+      continue;
+    }
+    if (!strcmp (a, "--stream")) continue;                        /* inputs are mapped and parsed in one go */
+    if (!strcmp (a, "--index")) { create_index = 1; continue; }
+    if (!strcmp (a, "-D")) { debug += 1; continue; }
+    if (a[0] == '-' && a[1]) print_help (1);                      /* unknown option; a lone "-" would be stdin */
+    if (n_inputs < MAX_INPUTS) inputs[n_inputs++] = a;
   }
+  wordlength = (unsigned int) v_word;
+  min = (unsigned int) v_min;
+  max = (unsigned int) v_max;
+  nthreads = (unsigned int) v_threads;
+  ntables = (unsigned int) v_tables;
+  tablesize = (unsigned long long) v_tsize;
+
   (void) nthreads;
   (void) ntables;
 

@@ -22,6 +22,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "gt4gpu_device.cuh"
 #include "gt4gpu_internal.h"
 
 namespace gt4gpu {
@@ -49,24 +50,7 @@ constexpr uint64_t ST_INCLUSIVE = 2ull << 62;
 constexpr int TAG_SHIFT = 56;
 constexpr uint64_t VALUE_MASK = (1ull << TAG_SHIFT) - 1;
 
-__device__ __forceinline__ uint64_t ld_relaxed (const uint64_t *p)
-{
-  uint64_t v;
-  asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void st_relaxed (uint64_t *p, uint64_t v)
-{
-  asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ uint64_t warp_sum_u64 (uint64_t v)
-{
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync (0xffffffffu, v, off);
-  return v;
-}
+using namespace dev;
 
 // ------------------------------------------------------------------------------------------
 // histograms of all digits in one pass over the keys
@@ -357,61 +341,10 @@ constexpr int RLE_WARPS = RLE_NT / 32;
 constexpr int RLE_ITEMS = GT4_RLE_ITEMS;
 constexpr int RLE_TILE = RLE_NT * RLE_ITEMS;
 
-constexpr uint64_t DESC_PARTIAL = 1ull << 62;
-constexpr uint64_t DESC_INCLUSIVE = 2ull << 62;
-constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1;
-
-// All 32 lanes of one warp; exclusive prefix of `aggregate` over the tiles.  One hop inspects RLE_LB_W rows of 32
-// descriptors (row k, lane l -> tile pred - 32 k - l), nearest first: with several hundred tiles in flight the nearest
-// tile that already knows its prefix is often more than 32 tiles back, and every hop costs an L2 round trip.  Only a
-// descriptor nearer than the nearest inclusive one can make the warp wait, and then only its row is polled again.
 #ifndef GT4_RLE_LB_W
-#define GT4_RLE_LB_W 4
+#define GT4_RLE_LB_W 4      // rows of 32 descriptors per look-back hop (gt4gpu_device.cuh)
 #endif
 constexpr int RLE_LB_W = GT4_RLE_LB_W;
-
-__device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t tile, uint64_t aggregate, int lane)
-{
-  if (tile == 0) {
-    if (lane == 0) st_relaxed (desc, DESC_INCLUSIVE | aggregate);
-    return 0;
-  }
-  if (lane == 0) st_relaxed (desc + tile, DESC_PARTIAL | aggregate);
-  uint64_t lane_sum = 0;
-  int64_t pred = (int64_t) tile - 1 - lane;
-  bool done = false;
-  while (!done) {
-    uint64_t d[RLE_LB_W];
-#pragma unroll
-    for (int k = 0; k < RLE_LB_W; k++) d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
-#pragma unroll
-    for (int k = 0; k < RLE_LB_W; k++) {
-      if (done) break;
-      while (true) {
-        const uint32_t st = (uint32_t) (d[k] >> 62);
-        const uint32_t m_wait = __ballot_sync (0xffffffffu, st == 0);
-        const uint32_t m_incl = __ballot_sync (0xffffffffu, st == 2);
-        const uint32_t m_stop = m_wait | m_incl;
-        if (m_stop == 0) {                     // a full row of partial counts
-          lane_sum += d[k] & DESC_VALUE_MASK;
-          break;
-        }
-        const int first = __ffs (m_stop) - 1;
-        if ((m_wait >> first) & 1u) {          // the nearest stopper has not posted yet: poll this row again
-          d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
-          continue;
-        }
-        if (lane <= first) lane_sum += d[k] & DESC_VALUE_MASK;
-        done = true;
-        break;
-      }
-    }
-    pred -= 32 * RLE_LB_W;
-  }
-  const uint64_t exclusive = warp_sum_u64 (lane_sum);
-  if (lane == 0) st_relaxed (desc + tile, DESC_INCLUSIVE | (exclusive + aggregate));
-  return exclusive;
-}
 
 __global__ void __launch_bounds__ (RLE_NT, GT4_RLE_MIN_CTAS)
 rle_heads_kernel (const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ words, uint64_t *__restrict__ first,
@@ -421,7 +354,7 @@ rle_heads_kernel (const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__res
   __shared__ uint64_t s_base;
   __shared__ uint32_t s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = (debug & 32) ? blockIdx.x : atomicAdd (ticket, 1u);
+  if (tid == 0) s_tile = atomicAdd (ticket, 1u);
   __syncthreads ();
   const uint64_t tile = s_tile;
   const uint64_t base = tile * RLE_TILE + (uint64_t) warp * 32 * RLE_ITEMS;
@@ -457,7 +390,7 @@ rle_heads_kernel (const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__res
     }
     const uint32_t tile_cnt = __shfl_sync (0xffffffffu, incl, RLE_WARPS - 1);
     if (lane < RLE_WARPS) s_wcnt[lane] = incl - v;
-    const uint64_t excl = (debug & 16) ? tile * RLE_TILE : lookback_exclusive (desc, tile, tile_cnt, lane);
+    const uint64_t excl = (debug & 16) ? tile * RLE_TILE : lookback_exclusive<RLE_LB_W> (desc, tile, tile_cnt, lane);
     if (lane == 0) {
       s_base = excl;
       if ((tile + 1) * RLE_TILE >= n) *n_unique = excl + tile_cnt;     // the last tile knows the total
@@ -545,7 +478,7 @@ static cudaError_t radix_sort_impl (uint64_t *keys, uint64_t *alt, uint32_t *val
     a.desc = desc;
     a.ticket = tickets + p;
     a.vin = vsrc; a.vout = vdst;
-    a.debug = getenv ("GT4GPU_DEBUG") ? atoi (getenv ("GT4GPU_DEBUG")) : 0;
+    a.debug = debug_flags ();
     if (vals) radix_onesweep_kernel<true><<<(unsigned) n_tiles, SORT_NT, smem, st>>> (a);
     else radix_onesweep_kernel<false><<<(unsigned) n_tiles, SORT_NT, smem, st>>> (a);
     uint64_t *t = src; src = dst; dst = t;
@@ -591,8 +524,7 @@ cudaError_t launch_rle_heads (const uint64_t *sorted, uint64_t n, uint64_t *word
   uint32_t *ticket = reinterpret_cast<uint32_t *> (scratch + 8);
   uint64_t *desc = reinterpret_cast<uint64_t *> (scratch + 256);
   (void) sm_count;     // one CTA per tile: a persistent loop over tickets measured slower (the next CTA's loads overlap the stores)
-  rle_heads_kernel<<<(unsigned) n_tiles, RLE_NT, 0, st>>> (sorted, n, words_tmp, first, desc, ticket, *d_n_unique,
-                                                         getenv ("GT4GPU_DEBUG") ? atoi (getenv ("GT4GPU_DEBUG")) : 0);
+  rle_heads_kernel<<<(unsigned) n_tiles, RLE_NT, 0, st>>> (sorted, n, words_tmp, first, desc, ticket, *d_n_unique, debug_flags ());
   return cudaGetLastError ();
 }
 

@@ -32,6 +32,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gt4gpu_device.cuh"
 #include "gt4gpu_internal.h"
 
 namespace gt4gpu {
@@ -44,9 +45,7 @@ namespace {
 constexpr int STORE_WARPS = GT4_STORE_WARPS;
 constexpr uint64_t TILE_END = ~0ull;
 
-constexpr uint64_t DESC_PARTIAL = 1ull << 62;
-constexpr uint64_t DESC_INCLUSIVE = 2ull << 62;
-constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1;
+using namespace dev;
 
 // NC consumer threads (warps 0 .. NC/32-1), then the producer warp, the look-back warp and the store warps
 template <int NC, int VT, int S>
@@ -143,33 +142,14 @@ __device__ __forceinline__ void fence_mbar_init () { asm volatile ("fence.mbarri
 template <int NC>
 __device__ __forceinline__ void consumer_sync () { asm volatile ("bar.sync 1, %0;" :: "n"(NC) : "memory"); }
 
-__device__ __forceinline__ uint64_t ld_relaxed (const uint64_t *p)
-{
-  uint64_t v;
-  asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void st_relaxed (uint64_t *p, uint64_t v)
-{
-  asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ uint64_t warp_sum_u64 (uint64_t v)
-{
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync (0xffffffffu, v, off);
-  return v;
-}
-
 // All 32 lanes of the look-back warp; returns the exclusive prefix of `aggregate`.
 //
 // The chain of prefixes has to advance as fast as tiles are produced (~50-100 tiles/us at the HBM
 // roofline) and every hop costs an L2 round trip, so one hop inspects LB_W rows of 32 descriptors
 // (row k, lane l -> tile pred - 32 k - l: every row is one coalesced 256-byte request) instead of
 // the textbook single row.  Rows are consumed nearest-first; only a descriptor NEARER than the
-// nearest inclusive one can make the warp wait, and then only its row is polled again, with a
-// back-off, so that the few cache lines around the frontier are not hammered by every CTA.
+// nearest inclusive one can make the warp wait, and then only its row is polled again (the shared
+// implementation is lookback_exclusive<W> in gt4gpu_device.cuh).
 #ifndef GT4_LB_W
 #define GT4_LB_W 4
 #endif
@@ -177,56 +157,18 @@ constexpr int LB_W = GT4_LB_W;
 
 struct LookbackStats { unsigned long long cycles, polls, hops, calls; };
 
-__device__ __forceinline__ uint64_t lookback_exclusive (uint64_t *desc, uint64_t tile, uint64_t aggregate, int lane, LookbackStats *stats = nullptr)
+__device__ __forceinline__ uint64_t lookback_with_stats (uint64_t *desc, uint64_t tile, uint64_t aggregate, int lane, LookbackStats *stats)
 {
-  const long long t_begin = stats ? clock64 () : 0;
+  if (!stats) return lookback_exclusive<LB_W> (desc, tile, aggregate, lane);
+  const long long t_begin = clock64 ();
   unsigned polls = 0, hops = 0;
-  if (tile == 0) {
-    if (lane == 0) st_relaxed (desc, DESC_INCLUSIVE | aggregate);
-    return 0;
-  }
-  if (lane == 0) st_relaxed (desc + tile, DESC_PARTIAL | aggregate);
-  uint64_t lane_sum = 0;
-  int64_t pred = (int64_t) tile - 1 - lane;
-  bool done = false;
-  while (!done) {
-    uint64_t d[LB_W];
-#pragma unroll
-    for (int k = 0; k < LB_W; k++) d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
-#pragma unroll
-    for (int k = 0; k < LB_W; k++) {
-      if (done) break;
-      while (true) {
-        const uint32_t st = (uint32_t) (d[k] >> 62);
-        const uint32_t m_wait = __ballot_sync (0xffffffffu, st == 0);
-        const uint32_t m_incl = __ballot_sync (0xffffffffu, st == 2);
-        const uint32_t m_stop = m_wait | m_incl;
-        if (m_stop == 0) {                     // a full row of partial counts
-          lane_sum += d[k] & DESC_VALUE_MASK;
-          break;
-        }
-        const int first = __ffs (m_stop) - 1;
-        if ((m_wait >> first) & 1u) {          // the nearest stopper has not posted yet: poll this row again
-          polls++;
-          d[k] = (pred - 32 * k >= 0) ? ld_relaxed (desc + (pred - 32 * k)) : DESC_INCLUSIVE;
-          continue;
-        }
-        if (lane <= first) lane_sum += d[k] & DESC_VALUE_MASK;
-        done = true;
-        break;
-      }
-    }
-    pred -= 32 * LB_W;
-    hops++;
-  }
-  if (stats) {
+  const uint64_t exclusive = lookback_exclusive<LB_W> (desc, tile, aggregate, lane, &polls, &hops);
+  if (tile != 0) {
     stats->cycles += (unsigned long long) (clock64 () - t_begin);
     stats->polls += polls;
     stats->hops += hops;
     stats->calls += 1;
   }
-  const uint64_t exclusive = warp_sum_u64 (lane_sum);
-  if (lane == 0) st_relaxed (desc + tile, DESC_INCLUSIVE | (exclusive + aggregate));
   return exclusive;
 }
 
@@ -469,7 +411,7 @@ setop2_stream_kernel (const TileArgs args)
       if (it >= s_n_iter) break;                  // the END marker, not a tile
       const uint64_t tile = s_mail[s].tile;
       const uint64_t base = (args.debug & 1) ? tile * TILE
-                          : lookback_exclusive (args.desc, tile, (uint64_t) s_mail[s].cnt, lane, (args.debug & 2) ? &stats : nullptr);
+                          : lookback_with_stats (args.desc, tile, (uint64_t) s_mail[s].cnt, lane, (args.debug & 2) ? &stats : nullptr);
       if (lane == 0) {
         s_mail[s].base = base;
         mbar_arrive (&bar_base[s]);
