@@ -1342,12 +1342,14 @@ int gt4gpu_count_words (const uint64_t *words, uint64_t n_words, int on_device, 
   if ((rc = dev_alloc (&tmp.p[1], n * sizeof (uint64_t)))) return rc;
   if ((rc = dev_alloc (&tmp.p[2], sort_scratch_bytes (n)))) return rc;
   keys = (uint64_t *) tmp.p[0]; alt = (uint64_t *) tmp.p[1]; ws_sort = (unsigned char *) tmp.p[2];
-  CU (cudaMemcpyAsync (keys, words, n * sizeof (uint64_t), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  const uint64_t *input = keys;
+  if (on_device) input = words;          // sorted straight out of the caller's array (read only)
+  else CU (cudaMemcpyAsync (keys, words, n * sizeof (uint64_t), cudaMemcpyHostToDevice, st));
 
   for (int i = 0; i < 3; i++) if (!tl_ev[i]) CU (cudaEventCreate (&tl_ev[i]));
   CU (cudaEventRecord (tl_ev[0], st));
   uint64_t *sorted = nullptr;
-  CU (launch_radix_sort (keys, alt, n, n_pass, ws_sort, g_ctx.sm_count, &sorted, st));
+  CU (launch_radix_sort (input, keys, alt, n, n_pass, ws_sort, g_ctx.sm_count, &sorted, st));
   CU (cudaEventRecord (tl_ev[1], st));
   uint64_t *words_tmp = (sorted == keys) ? alt : keys;      // the buffer the sort no longer needs
   if ((rc = dev_alloc (&tmp.p[3], n * sizeof (uint64_t)))) return rc;

@@ -88,8 +88,8 @@ cudaError_t launch_lookup_sorted (const uint64_t *words, const uint32_t *counts,
 static constexpr int SORT_MAX_PASSES = 8;                                        // 8-bit digits of a 64-bit word
 static constexpr size_t SORT_SCRATCH_HEAD = 2 * SORT_MAX_PASSES * 256 * 8 + 256;  // histograms, bin starts, tickets
 size_t sort_scratch_bytes (uint64_t n);
-cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch, int sm_count,
-                               uint64_t **sorted, cudaStream_t st);
+cudaError_t launch_radix_sort (const uint64_t *input, uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch,
+                               int sm_count, uint64_t **sorted, cudaStream_t st);
 // same with a 32-bit payload per key; the first pass fills it with the key's index, so *sorted_vals is the sorting permutation
 cudaError_t launch_radix_sort_pairs (uint64_t *keys, uint64_t *alt, uint32_t *vals, uint32_t *valt, uint64_t n, int n_pass,
                                      unsigned char *scratch, int sm_count, uint64_t **sorted, uint32_t **sorted_vals, cudaStream_t st);

@@ -432,11 +432,12 @@ size_t sort_scratch_bytes (uint64_t n)
   return SORT_SCRATCH_HEAD + (size_t) n_tiles * RADIX * sizeof (uint64_t);
 }
 
-// Sorts n keys ascending on their low 8 * n_pass bits.  `keys` and `alt` are both n entries; the result lands in
-// keys when n_pass is even, in alt when odd (returned through *sorted).  scratch: sort_scratch_bytes (n), any content.
+// Sorts n keys ascending on their low 8 * n_pass bits (n_pass >= 1).  `keys` and `alt` are work buffers of n entries; the
+// keys are read from `input`, which is either `keys` itself or an array that is only read.  The result lands in one of
+// the two buffers (returned through *sorted).  scratch: sort_scratch_bytes (n), any content.
 // With vals / valt (n u32 each) every key drags a payload along: vals is filled by the first pass with the key's
 // original index, *sorted_vals is the permutation that sorts the input.
-static cudaError_t radix_sort_impl (uint64_t *keys, uint64_t *alt, uint32_t *vals, uint32_t *valt, uint64_t n, int n_pass,
+static cudaError_t radix_sort_impl (const uint64_t *input, uint64_t *keys, uint64_t *alt, uint32_t *vals, uint32_t *valt, uint64_t n, int n_pass,
                                     unsigned char *scratch, int sm_count, uint64_t **sorted, uint32_t **sorted_vals, cudaStream_t st)
 {
   *sorted = keys;
@@ -455,7 +456,7 @@ static cudaError_t radix_sort_impl (uint64_t *keys, uint64_t *alt, uint32_t *val
 
   uint64_t hist_grid = (uint64_t) sm_count * 2;
   if (hist_grid > (n + 511) / 512) hist_grid = (n + 511) / 512;
-  radix_hist_kernel<<<(unsigned) hist_grid, 512, 0, st>>> (keys, n, n_pass, hist);
+  radix_hist_kernel<<<(unsigned) hist_grid, 512, 0, st>>> (input, n, n_pass, hist);
   radix_bins_kernel<<<n_pass, RADIX, 0, st>>> (hist, bins);
 
   static bool configured = false;   // benign race: the attribute is idempotent
@@ -467,7 +468,9 @@ static cudaError_t radix_sort_impl (uint64_t *keys, uint64_t *alt, uint32_t *val
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  uint64_t *src = keys, *dst = alt;
+  // the first pass may read the caller's own array (input != keys): nothing is copied, nothing of the caller's is written
+  const uint64_t *src = input;
+  uint64_t *dst = (input == keys) ? alt : keys;
   uint32_t *vsrc = nullptr, *vdst = vals;      // the first pass writes the identity permutation's image into vals
   for (int p = 0; p < n_pass; p++) {
     SweepArgs a;
@@ -481,29 +484,29 @@ static cudaError_t radix_sort_impl (uint64_t *keys, uint64_t *alt, uint32_t *val
     a.debug = debug_flags ();
     if (vals) radix_onesweep_kernel<true><<<(unsigned) n_tiles, SORT_NT, smem, st>>> (a);
     else radix_onesweep_kernel<false><<<(unsigned) n_tiles, SORT_NT, smem, st>>> (a);
-    uint64_t *t = src; src = dst; dst = t;
+    src = dst;
+    dst = (dst == keys) ? alt : keys;
     if (vals) {
       vsrc = vdst;
       vdst = (vdst == vals) ? valt : vals;
     }
   }
-  *sorted = src;
+  *sorted = const_cast<uint64_t *> (src);       // one of keys / alt: n_pass >= 1
   if (sorted_vals) *sorted_vals = vsrc;
   return cudaGetLastError ();
 }
 
-cudaError_t launch_radix_sort (uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch, int sm_count,
-                               uint64_t **sorted, cudaStream_t st)
+cudaError_t launch_radix_sort (const uint64_t *input, uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch,
+                               int sm_count, uint64_t **sorted, cudaStream_t st)
 {
-  if (n_pass == 0) { *sorted = keys; return cudaSuccess; }
-  return radix_sort_impl (keys, alt, nullptr, nullptr, n, n_pass, scratch, sm_count, sorted, nullptr, st);
+  return radix_sort_impl (input, keys, alt, nullptr, nullptr, n, n_pass, scratch, sm_count, sorted, nullptr, st);
 }
 
 cudaError_t launch_radix_sort_pairs (uint64_t *keys, uint64_t *alt, uint32_t *vals, uint32_t *valt, uint64_t n, int n_pass,
                                      unsigned char *scratch, int sm_count, uint64_t **sorted, uint32_t **sorted_vals, cudaStream_t st)
 {
   if (n > 0xffffffffull) return cudaErrorInvalidValue;     // payloads are 32-bit indices
-  return radix_sort_impl (keys, alt, vals, valt, n, n_pass, scratch, sm_count, sorted, sorted_vals, st);
+  return radix_sort_impl (keys, keys, alt, vals, valt, n, n_pass, scratch, sm_count, sorted, sorted_vals, st);
 }
 
 size_t rle_scratch_bytes (uint64_t n)
