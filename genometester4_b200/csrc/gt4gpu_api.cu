@@ -1271,8 +1271,8 @@ int gt4gpu_fasta_words_device (const void *text, uint64_t n_bytes, uint32_t word
   *n_words = 0;
   const unsigned char *p = static_cast<const unsigned char *> (text);
   if (n_bytes == 0 || p[0] == 0) return 0;
-  if (p[0] == '@') return fail (GT4GPU_ERR_ARG, "FastQ images are read on the host (gt4gpu_sequence_words)");
-  if (p[0] != '>') return fail (GT4GPU_ERR_FORMAT, "invalid start tag '%c'", p[0]);          // src/fasta.c:136-139
+  const bool fastq = p[0] == '@';
+  if (!fastq && p[0] != '>') return fail (GT4GPU_ERR_FORMAT, "invalid start tag '%c'", p[0]);          // src/fasta.c:136-139
   if (const void *z = memchr (p, 0, (size_t) n_bytes)) n_bytes = (uint64_t) (static_cast<const unsigned char *> (z) - p);   // :107-118
   int rc = ensure_ready ();
   if (rc) return rc;
@@ -1288,10 +1288,21 @@ int gt4gpu_fasta_words_device (const void *text, uint64_t n_bytes, uint32_t word
   unsigned char *ws = (unsigned char *) tmp.p[2];
   CU (cudaMemcpyAsync (d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
   const uint64_t *d_n = nullptr;
-  CU (launch_fasta_codes (d_text, n_bytes, ws, d_codes, &d_n, st));
+  const uint32_t *d_bad = nullptr;
+  const uint64_t *d_lines = nullptr;
+  uint32_t malformed = 0;
+  uint64_t n_lines = 0;
+  if (fastq) CU (launch_fastq_codes (d_text, n_bytes, ws, d_codes, &d_n, &d_bad, &d_lines, st));
+  else CU (launch_fasta_codes (d_text, n_bytes, ws, d_codes, &d_n, st));
   uint64_t n_codes = 0;
   CU (cudaMemcpyAsync (&n_codes, d_n, sizeof (n_codes), cudaMemcpyDeviceToHost, st));
+  if (fastq) {
+    CU (cudaMemcpyAsync (&malformed, d_bad, sizeof (malformed), cudaMemcpyDeviceToHost, st));
+    CU (cudaMemcpyAsync (&n_lines, d_lines, sizeof (n_lines), cudaMemcpyDeviceToHost, st));
+  }
   CU (cudaStreamSynchronize (st));
+  if (fastq && (n_lines & 3) == 2) malformed = 1;        // the image stops on or inside a '+' line (src/fasta.c:203-214)
+  if (malformed) return fail (GT4GPU_ERR_FORMAT, "malformed FastQ record (gt4gpu_sequence_words reads the image up to it, like the reference)");
   if (n_codes > n_bytes) return fail (GT4GPU_ERR_CUDA, "sequence pass kept %llu codes of %llu bytes", (unsigned long long) n_codes, (unsigned long long) n_bytes);
   CU (launch_fasta_word_counts (d_codes, n_codes, word_length, ws, &d_n, st));
   uint64_t n = 0;

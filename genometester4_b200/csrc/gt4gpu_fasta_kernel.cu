@@ -16,6 +16,7 @@
 //   offsets_kernel             exclusive sum over the chunks (one CTA)
 //   fasta_text_kernel<EMIT>    writes the compacted code stream (0..3 nucleotide, 4 = restart): names and transparent
 //                              bytes are gone
+//   fastq_text_kernel<...>     the same three passes for four-line FastQ records: the state is the line number mod 4
 //   fasta_words_kernel<COUNT/EMIT>   a k-mer ends at code j iff codes j-k+1..j are nucleotides: count per chunk, then
 //                              (after offsets_kernel) write the canonical words in file order
 //
@@ -157,6 +158,77 @@ fasta_text_kernel (const uint8_t *__restrict__ text, uint64_t n, LineState *__re
   for (int i = 0; i < FA_BYTES; i++) if (i < (int) n_out) dst[i] = out[i];
 }
 
+// FastQ (src/fasta.c:191-217, :272-295): records are four lines -- "@name", the sequence, "+...", the quality -- so the
+// reader's state at a byte is its line number modulo 4, i.e. a prefix count of line ends.  Only sequence lines produce
+// codes (plus one restart per record); a line 0 that does not start with '@' or a line 2 that does not start with '+'
+// is where the reference's reader gives up: the kernel only raises *malformed and the caller hands such images to the
+// serial host reader, which reproduces the reference's partial result.
+//   MODE_LINES: newline count of the chunk.  MODE_COUNT / MODE_EMIT: carry = line number at the start of the chunk.
+template <int MODE>
+__global__ void __launch_bounds__ (FA_NT)
+fastq_text_kernel (const uint8_t *__restrict__ text, uint64_t n, uint32_t *__restrict__ newlines, const uint64_t *__restrict__ line0,
+                   uint32_t *__restrict__ counts, const uint64_t *__restrict__ offsets, uint8_t *__restrict__ codes,
+                   uint32_t *__restrict__ malformed)
+{
+  __shared__ uint32_t s_sum[FA_NT / 32];
+  const int tid = threadIdx.x;
+  const uint64_t base = (uint64_t) blockIdx.x * FA_CHUNK + (uint64_t) tid * FA_BYTES;
+  uint8_t ch[FA_BYTES];
+  if (base + FA_BYTES <= n && (reinterpret_cast<uintptr_t> (text + base) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4 *> (text + base);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < FA_BYTES; i++) ch[i] = (uint8_t) (w[i >> 2] >> (8 * (i & 3)));
+  } else {
+#pragma unroll
+    for (int i = 0; i < FA_BYTES; i++) ch[i] = (base + i < n) ? text[base + i] : (uint8_t) 1;    // padding: a transparent control character
+  }
+  uint32_t n_nl = 0;
+#pragma unroll
+  for (int i = 0; i < FA_BYTES; i++) n_nl += (ch[i] == '\n' && base + i < n) ? 1u : 0u;
+  uint32_t total;
+  const uint32_t nl_before = block_exclusive_sum (n_nl, s_sum, &total);
+  if (MODE == MODE_LINES) {
+    if (tid == 0) newlines[blockIdx.x] = total;
+    return;
+  }
+  __syncthreads ();                   // s_sum is reused below
+  uint64_t line = line0[blockIdx.x] + nl_before;
+  bool at_line_start = base == 0 || (base <= n && text[base - 1] == '\n');
+  uint8_t out[FA_BYTES];
+  uint32_t n_out = 0;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < FA_BYTES; i++) {
+    if (base + i >= n) break;
+    const uint8_t c = ch[i];
+    const unsigned phase = (unsigned) (line & 3u);
+    if (at_line_start) {
+      if (phase == 0 && c != '@') bad = true;       // :284-287
+      if (phase == 2 && c != '+') bad = true;       // :203-206
+    }
+    at_line_start = false;
+    if (c == '\n') {
+      if (phase == 1) out[n_out++] = CODE_BREAK;     // the next record starts a new word (its name end resets the reader, :152-156)
+      line++;
+      at_line_start = true;
+    } else if (phase == 1) {
+      const uint8_t k = classify (c);
+      if (k <= 3) out[n_out++] = k;
+      else if (k == CODE_BREAK || k == CODE_GT) out[n_out++] = CODE_BREAK;   // '>' is an ordinary character in FastQ
+    }
+  }
+  if (bad) atomicOr (malformed, 1u);
+  const uint32_t at = block_exclusive_sum (n_out, s_sum, &total);
+  if (MODE == MODE_COUNT) {
+    if (tid == 0) counts[blockIdx.x] = total;
+    return;
+  }
+  uint8_t *dst = codes + offsets[blockIdx.x] + at;
+#pragma unroll
+  for (int i = 0; i < FA_BYTES; i++) if (i < (int) n_out) dst[i] = out[i];
+}
+
 // exclusive scan of the chunks' line states; one CTA of 1024 threads, each owning a contiguous run of chunks
 __global__ void __launch_bounds__ (1024)
 line_carry_kernel (const LineState *__restrict__ lines, uint64_t n_chunks, LineState *__restrict__ carry)
@@ -256,8 +328,8 @@ fasta_words_kernel (const uint8_t *__restrict__ codes, uint64_t n_codes, unsigne
 // ------------------------------------------------------------------------------------------
 uint64_t fasta_chunks (uint64_t n) { return (n + FA_CHUNK - 1) / FA_CHUNK; }
 
-// scratch per chunk: line state (8) + carry (8) + count (4) + offset (8, one extra)
-size_t fasta_scratch_bytes (uint64_t n_chunks) { return (size_t) (n_chunks + 1) * 32; }
+// scratch per chunk: line state (8) + carry (8) + count (4) + offset (8, one extra); FastQ: line number (8) + offset (8) + 2 counts (8) + flag
+size_t fasta_scratch_bytes (uint64_t n_chunks) { return (size_t) (n_chunks + 2) * 32; }
 
 // text (device, n bytes) -> codes (device, capacity n + n_chunks... at most one code per byte); *d_n_codes (device u64) is
 // offsets[n_chunks] inside the scratch
@@ -276,6 +348,32 @@ cudaError_t launch_fasta_codes (const uint8_t *text, uint64_t n, unsigned char *
   offsets_kernel<<<1, 1024, 0, st>>> (counts, nc, offsets);
   fasta_text_kernel<MODE_EMIT><<<(unsigned) nc, FA_NT, 0, st>>> (text, n, nullptr, carry, nullptr, offsets, codes);
   *d_n_codes = offsets + nc;
+  return cudaGetLastError ();
+}
+
+// FastQ text -> codes; *d_malformed (device u32) is non-zero when a record line starts with the wrong tag; *d_n_lines
+// (device u64) is the number of line ends, from which the caller sees an image that stops inside a '+' line
+cudaError_t launch_fastq_codes (const uint8_t *text, uint64_t n, unsigned char *scratch, uint8_t *codes, const uint64_t **d_n_codes,
+                                const uint32_t **d_malformed, const uint64_t **d_n_lines, cudaStream_t st)
+{
+  const uint64_t nc = fasta_chunks (n);
+  if (nc == 0 || nc > 0x7fffffffull) return nc ? cudaErrorInvalidConfiguration : cudaSuccess;
+  // scratch: line0 u64 [nc + 1] | offsets u64 [nc + 1] | newlines u32 [nc] | counts u32 [nc] | malformed u32
+  uint64_t *line0 = reinterpret_cast<uint64_t *> (scratch);
+  uint64_t *offsets = line0 + (nc + 1);
+  uint32_t *newlines = reinterpret_cast<uint32_t *> (offsets + (nc + 1));
+  uint32_t *counts = newlines + nc;
+  uint32_t *malformed = counts + nc;
+  cudaError_t e = cudaMemsetAsync (malformed, 0, sizeof (uint32_t), st);
+  if (e != cudaSuccess) return e;
+  fastq_text_kernel<MODE_LINES><<<(unsigned) nc, FA_NT, 0, st>>> (text, n, newlines, nullptr, nullptr, nullptr, nullptr, nullptr);
+  offsets_kernel<<<1, 1024, 0, st>>> (newlines, nc, line0);
+  fastq_text_kernel<MODE_COUNT><<<(unsigned) nc, FA_NT, 0, st>>> (text, n, nullptr, line0, counts, nullptr, nullptr, malformed);
+  offsets_kernel<<<1, 1024, 0, st>>> (counts, nc, offsets);
+  fastq_text_kernel<MODE_EMIT><<<(unsigned) nc, FA_NT, 0, st>>> (text, n, nullptr, line0, nullptr, offsets, codes, malformed);
+  *d_n_codes = offsets + nc;
+  *d_malformed = malformed;
+  *d_n_lines = line0 + nc;          // line ends in the whole image
   return cudaGetLastError ();
 }
 

@@ -104,6 +104,8 @@ uint64_t fasta_chunks (uint64_t n);
 size_t fasta_scratch_bytes (uint64_t n_chunks);
 cudaError_t launch_fasta_codes (const uint8_t *text, uint64_t n, unsigned char *scratch, uint8_t *codes, const uint64_t **d_n_codes,
                                 cudaStream_t st);
+cudaError_t launch_fastq_codes (const uint8_t *text, uint64_t n, unsigned char *scratch, uint8_t *codes, const uint64_t **d_n_codes,
+                                const uint32_t **d_malformed, const uint64_t **d_n_lines, cudaStream_t st);
 cudaError_t launch_fasta_word_counts (const uint8_t *codes, uint64_t n_codes, unsigned k, unsigned char *scratch,
                                       const uint64_t **d_n_words, cudaStream_t st);
 cudaError_t launch_fasta_words (const uint8_t *codes, uint64_t n_codes, unsigned k, const unsigned char *scratch, uint64_t *words,

@@ -5,8 +5,8 @@
  * Flag grammar, validation order, messages, the "<out>_<k>.list" name, tmp + rename and exit codes follow main()
  * of /root/reference/src/glistmaker.c:138-366 (help text :1303-1326).  The pipeline mirrors the reference's tasks:
  *
- *   read_table      (:893-968)    sequence file -> a table of canonical words        gt4gpu_fasta_words_device (GPU; FastA)
- *                                                                                     gt4gpu_sequence_words (host; FastQ)
+ *   read_table      (:893-968)    sequence file -> a table of canonical words        gt4gpu_fasta_words_device (GPU)
+ *                                                                                     gt4gpu_sequence_words (host: malformed FastQ)
  *   wordtable_sort + merge_tables_to_file (:924, :1080-1144)   table -> (word, count)  gt4gpu_count_words   (GPU)
  *   collate_files / final gt4_write_union (:787-835, :314-333)  tables -> one list     gt4gpu_union_multi   (GPU)
  *
@@ -71,6 +71,7 @@ static gt4gpu_list *table_lists[4096];
 static unsigned n_tables = 0;
 static double t_read = 0, t_sort = 0, t_collate = 0;
 static uint64_t fasta_block = 1ULL << 30;     /* bytes of FastA text parsed per GPU call (GT4GPU_FASTA_BLOCK overrides) */
+static uint64_t fastq_device_max = 8ULL << 30;   /* larger FastQ files take the host reader */
 static unsigned long long n_read = 0;
 
 static int
@@ -267,6 +268,33 @@ main (int argc, const char *argv[])
       }
       continue;
     }
+    if (text[0] == '@' && (uint64_t) s.st_size <= fastq_device_max) {
+      /* FastQ: well-formed four-line records are parsed on the GPU in one go; anything the reference's reader would give
+       * up on (GT4GPU_ERR_FORMAT) goes to the serial reader below, which keeps the words up to that point like glistmaker */
+      uint64_t n_block = 0, taken = 0;
+      uint64_t *d_words = NULL;
+      int rc = gt4gpu_fasta_words_device (text, (uint64_t) s.st_size, wordlength, &d_words, &n_block);
+      if (rc == 0) {
+        t_read += now () - t0;
+        n_read += n_block;
+        while (!rc && taken < n_block) {
+          uint64_t take = n_block - taken < tablesize ? n_block - taken : tablesize;
+          rc = flush_table (d_words + taken, take, 1, wordlength);
+          taken += take;
+        }
+        gt4gpu_device_free (d_words);
+        munmap ((void *) text, s.st_size);
+        if (rc) {
+          fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
+          return 1;
+        }
+        continue;
+      }
+      if (rc != GT4GPU_ERR_FORMAT) {
+        fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
+        return 1;
+      }
+    }
     uint64_t *words = (uint64_t *) malloc ((size_t) s.st_size * sizeof (uint64_t) + 8);
     if (!words) {
       fprintf (stderr, "Out of memory reading %s\n", inputs[i]);
@@ -351,8 +379,8 @@ gpu_error:
     fprintf (stderr, "Cannot rename %s to %s\n", tmp_name, out_name);
   }
   if (debug) {
-    fprintf (stderr, "Read %llu words at %.2f (%u words/s)\n", n_read, t_read, (unsigned int) (n_read / (t_read > 0 ? t_read : 1e-9)));
-    fprintf (stderr, "Sort %llu words at %.2f (%u words/s)\n", n_read, t_sort, (unsigned int) (n_read / (t_sort > 0 ? t_sort : 1e-9)));
+    fprintf (stderr, "Read %llu words at %.2f (%.0f words/s)\n", n_read, t_read, n_read / (t_read > 0 ? t_read : 1e-9));
+    fprintf (stderr, "Sort %llu words at %.2f (%.0f words/s)\n", n_read, t_sort, n_read / (t_sort > 0 ? t_sort : 1e-9));
     fprintf (stderr, "Collate and write %u tables at %.2f\n", n_tables, t_collate);
   }
   for (i = 0; i < n_tables; i++) {

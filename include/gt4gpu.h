@@ -199,10 +199,12 @@ int gt4gpu_lookup (const gt4gpu_list *list, const uint64_t *queries, uint64_t n_
  * the words read so far, as glistmaker keeps them.  No device work. */
 int gt4gpu_sequence_words (const void *text, uint64_t n_bytes, uint32_t word_length, uint64_t *words, uint64_t capacity,
                            uint64_t *n_words);
-/* Device form of gt4gpu_sequence_words for FastA images: text is a HOST buffer holding the file image; the canonical
- * words come back as a library-owned DEVICE array in file order (release it with gt4gpu_device_free), ready for
- * gt4gpu_count_words (..., on_device = 1, ...).  Same acceptance rules as the host reader; FastQ images return
- * GT4GPU_ERR_ARG (read them with gt4gpu_sequence_words).  *d_words is NULL when the image holds no k-mer. */
+/* Device form of gt4gpu_sequence_words: text is a HOST buffer holding a FastA or FastQ file image; the canonical words
+ * come back as a library-owned DEVICE array in file order (release it with gt4gpu_device_free), ready for
+ * gt4gpu_count_words (..., on_device = 1, ...).  FastA: same acceptance rules as the host reader.  FastQ: well-formed
+ * four-line records only; an image the reference's reader would give up on returns GT4GPU_ERR_FORMAT and no words --
+ * gt4gpu_sequence_words then yields the words up to that point, as glistmaker keeps them.  *d_words is NULL when the
+ * image holds no k-mer. */
 int gt4gpu_fasta_words_device (const void *text, uint64_t n_bytes, uint32_t word_length, uint64_t **d_words, uint64_t *n_words);
 void gt4gpu_device_free (void *d_ptr);
 

@@ -6,6 +6,9 @@ import numpy as np
 import genometester4_b200 as g
 from genometester4_b200 import synth, api
 g.init(0)
+def rand_bytes(rng, alphabet: bytes, n) -> bytes:
+    """n random characters of `alphabet` (one byte each: bytes() of an int64 array would be its raw 8-byte image)."""
+    return rng.choice(np.frombuffer(alphabet, dtype=np.uint8), size=int(n)).tobytes()
 (wa, ca), (wb, cb) = synth.pair_numpy(42, 25, 60_000, 0, 60_000, 1 / 3, 1 / 3)
 la, lb = g.WordList.from_arrays(wa, ca, 25), g.WordList.from_arrays(wb, cb, 25)
 for shape in (51209, 25607):
@@ -31,7 +34,7 @@ for k, n in ((5, 1), (16, 8191), (25, 8193), (32, 40_000)):
     assert int(c.sum()) == n
     lst = g.WordList.from_arrays(w, c, k)
     g.lookup(lst, rng.integers(0, hi, size=3001, dtype=np.uint64))
-for text in (b">a\nACGT", b">x\n" + bytes(rng.choice(list(b"ACGTN\n"), size=20_001)) + b"\n>y z\n" + bytes(rng.choice(list(b"ACGT"), size=4095)),
+for text in (b">a\nACGT", b">x\n" + rand_bytes(rng, b"ACGTN\n", 20_001) + b"\n>y z\n" + rand_bytes(rng, b"ACGT", 4095),
              b">" + b"n" * 5000 + b"\n" + b"ACGT" * 2500):
     for k in (1, 13, 32):
         d = g.fasta_words_device(text, k)

@@ -5,6 +5,11 @@ import os
 import numpy as np
 import pytest
 
+
+def rand_bytes(rng, alphabet: bytes, n) -> bytes:
+    """n random characters of `alphabet` (one byte each: bytes() of an int64 array would be its raw 8-byte image)."""
+    return rng.choice(np.frombuffer(alphabet, dtype=np.uint8), size=int(n)).tobytes()
+
 pytestmark = pytest.mark.gpu
 
 SORT_TILE = 512 * 16     # keys per CTA of radix_onesweep_kernel
@@ -159,8 +164,8 @@ def test_device_fasta_reader_matches_host_reader(g, oracle):
     for _ in range(6):            # random images whose names, lines and N runs straddle the 4 KiB chunks in every way
         parts = []
         for r in range(int(rng.integers(1, 60))):
-            name = bytes(rng.choice(list(b"abc >XYZ"), size=int(rng.integers(0, 300))))
-            seq = bytes(rng.choice(list(b"ACGTACGTACGTNacgtn\n\n\r -"), size=int(rng.integers(0, 9000))))
+            name = rand_bytes(rng, b"abc >XYZ", rng.integers(0, 300))
+            seq = rand_bytes(rng, b"ACGTACGTACGTNacgtn\n\n\r -", rng.integers(0, 9000))
             parts.append(b">" + name.replace(b"\n", b"") + b"\n" + seq)
             if rng.random() < 0.2:
                 parts.append(b">inline" * int(rng.integers(1, 4)))
@@ -172,10 +177,10 @@ def test_device_fasta_reader_matches_host_reader(g, oracle):
             assert dev.n_words == host.size, (text[:60], k)
             assert np.array_equal(dev.to_host(), host), (text[:60], k)
             dev.free()
-    for bad, code in ((b"x", 3), (b"ACGT\n", 3), (b"@r\nACGT\n+\nIIII\n", 1)):
+    for bad in (b"x", b"ACGT\n"):
         with pytest.raises(g.GT4GPUError) as e:
             g.fasta_words_device(bad, 4)
-        assert e.value.code == code
+        assert e.value.code == 3
     assert g.fasta_words_device(b"", 4).n_words == 0
 
 
@@ -192,3 +197,39 @@ def test_device_fasta_to_list_medium(g, oracle):
     exp = oracle.count_words(oracle.sequence_words(text, k), k)
     w, c = res.to_host()
     assert np.array_equal(w, exp.words) and np.array_equal(c, exp.counts)
+
+
+def test_device_fastq_reader_matches_host_reader(g, oracle):
+    """Four-line FastQ records on the GPU (state = line number mod 4) == the byte-serial reader; every image the
+    reference's reader gives up on is refused with GT4GPU_ERR_FORMAT instead."""
+    from pathlib import Path
+    gold_dir = Path(__file__).parent / "golden" / "maker"
+    rng = np.random.default_rng(31)
+
+    def record(i, n, crlf=False):
+        seq = rand_bytes(rng, b"ACGTACGTACGTNacgt", n)
+        qual = rand_bytes(rng, b"IJK>@+#!~", n)
+        nl = b"\r\n" if crlf else b"\n"
+        return b"@read%d some text" % i + nl + seq + nl + b"+" + (b"read%d" % i if i % 3 == 0 else b"") + nl + qual + nl
+
+    good = [(gold_dir / "reads.fq").read_bytes(),
+            b"@r\nACGT\n+\nIIII\n", b"@r\nACGT\n+\nIIII", b"@r\nACGT\n+\n", b"@r\nACGT", b"@r\n", b"@r",
+            b"@r\nAC>GT@AC\n+r\n>>@@\n@s\nGT\n+\nII\n",
+            b"".join(record(i, int(rng.integers(1, 400))) for i in range(300)),
+            b"".join(record(i, int(rng.integers(3000, 9000))) for i in range(12)),           # lines longer than a chunk
+            b"".join(record(i, 150, crlf=True) for i in range(200)),
+            b"".join(record(i, 100) for i in range(100))[:-37]]                              # stops inside a quality line
+    for text in good:
+        for k in (1, 4, 16, 25, 32):
+            host = oracle.sequence_words(text, k)
+            dev = g.fasta_words_device(text, k)
+            assert dev.n_words == host.size and np.array_equal(dev.to_host(), host), (text[:40], k)
+            dev.free()
+    bad = [b"@r\nACGT\nIIII\n", b"@r\nACGT\n+\nIIII\nX", b"@r\nACGT\n", b"@r\nACGT\n+abc", b"@r\nACGT\n+\nIIII\n\n",
+           b"".join(record(i, 80) for i in range(50)) + b"ACGT\n" + record(99, 80)]
+    for text in bad:
+        with pytest.raises(ValueError):
+            oracle.sequence_words(text, 2)
+        with pytest.raises(g.GT4GPUError) as e:
+            g.fasta_words_device(text, 2)
+        assert e.value.code == 3, text[:40]

@@ -9,6 +9,11 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+
+def rand_bytes(rng, alphabet: bytes, n) -> bytes:
+    """n random characters of `alphabet` (one byte each: bytes() of an int64 array would be its raw 8-byte image)."""
+    return rng.choice(np.frombuffer(alphabet, dtype=np.uint8), size=int(n)).tobytes()
+
 GOLD_DIR = Path(__file__).parent / "golden" / "maker"
 GOLD = json.loads((GOLD_DIR / "maker_golden.json").read_text())
 
@@ -31,7 +36,7 @@ def test_oracle_vs_live_glistmaker(oracle, tmp_path):
     if oracle.ref_binary("glistmaker") is None:
         pytest.skip("oracle/_ref/glistmaker not built here")
     rng = np.random.default_rng(99)
-    text = b"".join(b">r%d\n" % i + bytes(rng.choice(list(b"ACGTNacgt\n"), size=int(rng.integers(50, 900)))) + b"\n"
+    text = b"".join(b">r%d\n" % i + rand_bytes(rng, b"ACGTNacgt\n", rng.integers(50, 900)) + b"\n"
                     for i in range(40))
     (tmp_path / "x.fa").write_bytes(text)
     import subprocess
