@@ -57,7 +57,10 @@ struct StreamCfg {
   static constexpr int LOOKBACK_WARP0 = NC / 32 + 2;          // one look-back warp per stage
   static constexpr int STORE_WARP0 = LOOKBACK_WARP0 + S;
   static constexpr int NTHREADS = NC + 64 + 32 * S + 32 * STORE_WARPS;
-  static constexpr int GROUP = NC / 32;                       // consumer threads per coarse co-rank: one splitter round of 32 searches
+#ifndef GT4_SPLIT_POINTS
+#define GT4_SPLIT_POINTS 32
+#endif
+  static constexpr int GROUP = NC / GT4_SPLIT_POINTS;         // consumer threads per coarse co-rank (the splitter warp searches 32 co-ranks per round)
   static constexpr int NSPLIT = NC / GROUP + 1;
   static constexpr int MIN_CTAS = (NC <= 256) ? 2 : 1;
   static constexpr int TILE = CONSUMERS * VT;
