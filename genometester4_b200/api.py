@@ -327,8 +327,9 @@ class DeviceWords:
 
 
 def fasta_words_device(text: bytes, word_length: int) -> DeviceWords:
-    """FastA image (host bytes) -> canonical words in HBM, parsed on the GPU (fasta_reader_read_nwords,
-    src/fasta.c:88-290).  Feed ``.ptr`` / ``.n_words`` to :func:`count_words`."""
+    """FastA or FastQ image (host bytes) -> canonical words in HBM, parsed on the GPU (fasta_reader_read_nwords,
+    src/fasta.c:88-290).  Feed ``.ptr`` / ``.n_words`` to :func:`count_words`.  A FastQ image the reference's reader
+    would give up on raises GT4GPUError(code 3); :func:`sequence_words` reads such images up to that point."""
     ptr, n = C.c_void_p(), C.c_uint64()
     _check(_lib.load().gt4gpu_fasta_words_device(text, len(text), word_length, C.byref(ptr), C.byref(n)))
     return DeviceWords(ptr.value or 0, n.value, word_length)
