@@ -99,3 +99,46 @@ def test_lookup_device_arrays(g, oracle):
     ow, oc = oracle.lookup(oracle.SList(words, counts, k), q.cpu().numpy().astype(np.uint64))
     assert np.array_equal(out.cpu().numpy().astype(np.uint32), oc)
     assert np.array_equal(canon.cpu().numpy().astype(np.uint64), ow)
+
+
+def test_entry_points_are_reentrant(g, oracle):
+    """glistmaker calls gt4_write_union from several worker threads at once.  Four host threads
+    drive merges, list building and lookups concurrently (ctypes releases the GIL); every result must still be exact."""
+    import threading
+    k = 19
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for _ in range(6):
+                wa = np.unique(rng.integers(0, 4 ** k, size=60_000, dtype=np.uint64))
+                wb = np.unique(rng.integers(0, 4 ** k, size=50_000, dtype=np.uint64))
+                wb[:20_000] = wa[:20_000]
+                wb = np.unique(wb)
+                ca = rng.integers(1, 100, size=wa.size).astype(np.uint32)
+                cb = rng.integers(1, 100, size=wb.size).astype(np.uint32)
+                la, lb = g.WordList.from_arrays(wa, ca, k), g.WordList.from_arrays(wb, cb, k)
+                got = g.compare_wordmaps(la, lb, find_union=1, find_intrsec=1, cutoff=2)
+                want = oracle.compare2(oracle.SList(wa, ca, k), oracle.SList(wb, cb, k), union=True, intrsec=True, cutoff=2)
+                for s in ("union", "intrsec"):
+                    w, c = got[s].to_host()
+                    assert np.array_equal(w, want[s].words) and np.array_equal(c, want[s].counts)
+                raw = rng.integers(0, 4 ** 8, size=90_000, dtype=np.uint64)
+                res = g.count_words(raw, 8)
+                exp = oracle.count_words(raw, 8)
+                w, c = res.to_host()
+                assert np.array_equal(w, exp.words) and np.array_equal(c, exp.counts)
+                q = rng.integers(0, 4 ** k, size=30_000, dtype=np.uint64)
+                cw, cc = g.lookup(la, q)
+                ow, oc = oracle.lookup(oracle.SList(wa, ca, k), q)
+                assert np.array_equal(cw, ow) and np.array_equal(cc, oc)
+        except Exception as e:       # noqa: BLE001 -- reported below with the thread's seed
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
