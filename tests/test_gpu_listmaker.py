@@ -233,3 +233,33 @@ def test_device_fastq_reader_matches_host_reader(g, oracle):
         with pytest.raises(g.GT4GPUError) as e:
             g.fasta_words_device(text, 2)
         assert e.value.code == 3, text[:40]
+
+
+def test_device_readers_fuzz_against_oracle(g, oracle):
+    """Random images over a hostile alphabet: the device readers accept exactly what the reference's state machine
+    accepts (FastA always once the start tag is right; FastQ unless a record is malformed) and agree on every word."""
+    rng = np.random.default_rng(1618)
+    alphabet = np.frombuffer(b"ACGTacgtNn>@+\n\n\n\r \x00IJ-", dtype=np.uint8)
+    n_ok = n_err = 0
+    for case in range(2500):
+        n = int(rng.integers(0, 200)) if case % 5 else int(rng.integers(4000, 9000))      # some span several chunks
+        text = (b">" if case % 2 else b"@") + rng.choice(alphabet, size=n).tobytes()
+        k = int(rng.integers(1, 9))
+        try:
+            want = oracle.sequence_words(text, k)
+        except ValueError:
+            want = None
+        try:
+            dev = g.fasta_words_device(text, k)
+            got = dev.to_host()
+            dev.free()
+        except g.GT4GPUError as e:
+            assert e.code == 3
+            got = None
+        assert (want is None) == (got is None), (text[:80], k, len(text))
+        if want is not None:
+            assert np.array_equal(want, got), (text[:80], k)
+            n_ok += 1
+        else:
+            n_err += 1
+    assert n_ok > 500 and n_err > 300

@@ -119,3 +119,32 @@ def test_listmaker_cli_static_expectations():
     assert r.returncode == 1 and r.stderr.startswith(b"Error: Invalid word-length 40 (must be 1 - 32)!\n")
     r = subprocess.run([str(cli), "plain.fa", "-w", "16", "--index"], cwd=GOLD_DIR, capture_output=True)
     assert r.returncode == 1 and b"not supported" in r.stderr
+
+
+def test_host_sequence_reader_fuzz_against_oracle(oracle):
+    """3 000 short random images over a hostile alphabet (tags, line ends, NUL, non-nucleotides): the product's reader
+    and the oracle's restatement of the reference state machine must agree on acceptance and on every word."""
+    import genometester4_b200 as g
+    rng = np.random.default_rng(2718)
+    alphabet = np.frombuffer(b"ACGTacgtNn>@+\n\n\r \x00IJ-", dtype=np.uint8)
+    n_ok = n_err = 0
+    for case in range(3000):
+        body = rng.choice(alphabet, size=int(rng.integers(0, 120))).tobytes()
+        text = (b">" if case % 2 else b"@") + body if case % 7 else body
+        k = int(rng.integers(1, 9))
+        try:
+            want = oracle.sequence_words(text, k)
+        except ValueError:
+            want = None
+        try:
+            got = g.sequence_words(text, k)
+        except g.GT4GPUError as e:
+            assert e.code == 3
+            got = None
+        assert (want is None) == (got is None), (text, k)
+        if want is not None:
+            assert np.array_equal(want, got), (text, k)
+            n_ok += 1
+        else:
+            n_err += 1
+    assert n_ok > 500 and n_err > 500
