@@ -7,14 +7,16 @@
 //   radix_hist_kernel        one read of the keys: 256-bin histograms of every 8-bit digit that will
 //                            be sorted (only ceil(2k/8) digits: words are < 4^k)
 //   radix_bins_kernel        exclusive scan of each histogram -> first output slot of every bin
-//   radix_onesweep_kernel    one least-significant-digit pass: a tile of keys is ranked inside the
-//                            CTA (warp match + per-warp digit counters, stable), the per-digit tile
-//                            counts are chained across tiles by a decoupled look-back (256 chains in
-//                            parallel, one per thread), keys are regrouped by digit in shared memory
-//                            and leave in runs of consecutive addresses.  8 B read + 8 B written per
-//                            key and pass; no separate "upsweep" pass over the data.
+//   radix_onesweep_kernel    one least-significant-digit pass: a tile of 512 x 16 keys is ranked inside
+//                            the CTA (eight warp votes per key + per-warp digit counters, stable), the
+//                            per-digit tile counts are published and then chained across tiles by a
+//                            decoupled look-back (256 chains in parallel, one per thread) while the keys
+//                            are regrouped by digit in shared memory; they leave in runs of consecutive
+//                            addresses.  8 B read + 8 B written per key and pass; no separate "upsweep"
+//                            pass over the data.  <true>: every key drags a 32-bit payload along (the
+//                            key's position: the sorting permutation, used by the lookup batches).
 //   rle_heads_kernel         sorted keys -> distinct words + index of each run's first element
-//                            (block scan + decoupled look-back)
+//                            (warp votes, block scan, decoupled look-back)
 //   rle_counts_kernel        count = distance to the next run's first element
 //
 // Integer work, HBM-bound; no tensor cores.
