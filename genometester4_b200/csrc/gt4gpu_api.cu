@@ -541,19 +541,49 @@ int download_aos (const uint64_t *d_words, const uint32_t *d_counts, uint64_t n,
   return rc;
 }
 
-int write_all (int fd, const void *buf, size_t bytes, int64_t offset)
+static int write_span (int fd, const unsigned char *p, size_t bytes, int64_t offset)
 {
-  const unsigned char *p = static_cast<const unsigned char *> (buf);
   while (bytes) {
     ssize_t w = (offset >= 0) ? pwrite (fd, p, bytes, offset) : write (fd, p, bytes);
     if (w < 0) {
       if (errno == EINTR) continue;
-      return fail (GT4GPU_ERR_IO, "write failed: %s", strerror (errno));
+      return errno ? errno : EIO;
     }
     p += w;
     bytes -= (size_t) w;
     if (offset >= 0) offset += w;
   }
+  return 0;
+}
+
+// offset < 0: sequential write at the descriptor's position.  Large spans to a seekable file are cut into pieces written
+// with pwrite from a few threads (one thread copies into the page cache at 3-4 GB/s only).
+int write_all (int fd, const void *buf, size_t bytes, int64_t offset)
+{
+  const unsigned char *p = static_cast<const unsigned char *> (buf);
+  constexpr size_t PARALLEL_MIN = 64u << 20;
+  constexpr unsigned N_THREADS = 4;
+  if (bytes >= PARALLEL_MIN) {
+    const int64_t at = (offset >= 0) ? offset : (int64_t) lseek (fd, 0, SEEK_CUR);
+    if (at >= 0) {
+      int err[N_THREADS] = {0, 0, 0, 0};
+      std::vector<std::thread> pool;
+      const size_t piece = ((bytes / N_THREADS) + 4095) & ~(size_t) 4095;
+      for (unsigned t = 0; t < N_THREADS; t++) {
+        const size_t lo = (size_t) t * piece;
+        if (lo >= bytes) break;
+        const size_t len = std::min (piece, bytes - lo);
+        pool.emplace_back ([=, &err] { err[t] = write_span (fd, p + lo, len, at + (int64_t) lo); });
+      }
+      for (auto &th : pool) th.join ();
+      for (unsigned t = 0; t < N_THREADS; t++)
+        if (err[t]) return fail (GT4GPU_ERR_IO, "write failed: %s", strerror (err[t]));
+      if (offset < 0 && lseek (fd, at + (int64_t) bytes, SEEK_SET) < 0) return fail (GT4GPU_ERR_IO, "lseek failed: %s", strerror (errno));
+      return 0;
+    }
+  }
+  const int e = write_span (fd, p, bytes, offset);
+  if (e) return fail (GT4GPU_ERR_IO, "write failed: %s", strerror (e));
   return 0;
 }
 
