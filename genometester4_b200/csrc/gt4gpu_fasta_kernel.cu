@@ -25,42 +25,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gt4gpu_fasta_core.cuh"
 #include "gt4gpu_internal.h"
 
 namespace gt4gpu {
 
 namespace {
 
+using namespace reader;
+
 constexpr int FA_NT = 256;
-constexpr int FA_BYTES = 16;                       // bytes (or codes) per thread
+constexpr int FA_BYTES = BYTES_PER_THREAD;         // bytes (or codes) per thread
 constexpr int FA_CHUNK = FA_NT * FA_BYTES;         // 4 KiB per CTA
-constexpr uint8_t CODE_BREAK = 4, CODE_SKIP = 5, CODE_NL = 6, CODE_GT = 7;
 enum { MODE_LINES = 0, MODE_COUNT = 1, MODE_EMIT = 2 };
-
-__device__ __forceinline__ uint8_t classify (uint8_t c)
-{
-  switch (c) {
-  case 'A': case 'a': return 0;
-  case 'C': case 'c': return 1;
-  case 'G': case 'g': return 2;
-  case 'T': case 't': case 'U': case 'u': return 3;
-  case '\n': return CODE_NL;
-  case '>': return CODE_GT;
-  default: return c < ' ' ? CODE_SKIP : CODE_BREAK;
-  }
-}
-
-// Line state of a span of text: does it contain a line end, and is there a '>' after its last line end (anywhere, if it
-// has none).  combine (a, b) is the state of the concatenation "a b"; the operator is associative.
-struct LineState { uint32_t has_nl, gt; };
-
-__device__ __forceinline__ LineState combine (LineState a, LineState b)
-{
-  LineState r;
-  r.has_nl = a.has_nl | b.has_nl;
-  r.gt = b.has_nl ? b.gt : (a.gt | b.gt);
-  return r;
-}
 
 __device__ __forceinline__ uint32_t block_exclusive_sum (uint32_t v, uint32_t *s_warp, uint32_t *total)
 {
@@ -103,12 +80,7 @@ fasta_text_kernel (const uint8_t *__restrict__ text, uint64_t n, LineState *__re
     for (int i = 0; i < FA_BYTES; i++) cls[i] = (base + i < n) ? classify (text[base + i]) : CODE_SKIP;
   }
   // line state of this thread's 16 bytes, then of everything in the chunk before them
-  LineState mine = {0u, 0u};
-#pragma unroll
-  for (int i = 0; i < FA_BYTES; i++) {
-    if (cls[i] == CODE_NL) { mine.has_nl = 1u; mine.gt = 0u; }
-    else if (cls[i] == CODE_GT) mine.gt = 1u;
-  }
+  const LineState mine = span_state (cls, FA_BYTES);
   LineState incl = mine;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -131,22 +103,8 @@ fasta_text_kernel (const uint8_t *__restrict__ text, uint64_t n, LineState *__re
   if (lane == 0) { prev.has_nl = 0u; prev.gt = 0u; }
   const LineState cur0 = combine (carry[blockIdx.x], combine (before, prev));
 
-  // walk the bytes; in_name = "a '>' since the last line end"
-  bool in_name = cur0.gt != 0u;
   uint8_t out[FA_BYTES];
-  uint32_t n_out = 0;
-#pragma unroll
-  for (int i = 0; i < FA_BYTES; i++) {
-    const uint8_t k = cls[i];
-    if (k == CODE_NL) {
-      if (in_name) out[n_out++] = CODE_BREAK;      // the end of a name restarts the word (:152-156)
-      in_name = false;
-    } else if (k == CODE_GT) {
-      in_name = true;                              // a name starts (inside a name '>' is just a character)
-    } else if (!in_name && k <= CODE_BREAK) {
-      out[n_out++] = k;
-    }
-  }
+  const uint32_t n_out = (uint32_t) walk_fasta (cls, FA_BYTES, cur0, out);
   uint32_t total;
   const uint32_t at = block_exclusive_sum (n_out, s_sum, &total);
   if (MODE == MODE_COUNT) {
@@ -193,31 +151,12 @@ fastq_text_kernel (const uint8_t *__restrict__ text, uint64_t n, uint32_t *__res
     return;
   }
   __syncthreads ();                   // s_sum is reused below
-  uint64_t line = line0[blockIdx.x] + nl_before;
-  bool at_line_start = base == 0 || (base <= n && text[base - 1] == '\n');
+  const uint64_t line = line0[blockIdx.x] + nl_before;
+  const bool at_line_start = base == 0 || (base <= n && text[base - 1] == '\n');
   uint8_t out[FA_BYTES];
-  uint32_t n_out = 0;
   bool bad = false;
-#pragma unroll
-  for (int i = 0; i < FA_BYTES; i++) {
-    if (base + i >= n) break;
-    const uint8_t c = ch[i];
-    const unsigned phase = (unsigned) (line & 3u);
-    if (at_line_start) {
-      if (phase == 0 && c != '@') bad = true;       // :284-287
-      if (phase == 2 && c != '+') bad = true;       // :203-206
-    }
-    at_line_start = false;
-    if (c == '\n') {
-      if (phase == 1) out[n_out++] = CODE_BREAK;     // the next record starts a new word (its name end resets the reader, :152-156)
-      line++;
-      at_line_start = true;
-    } else if (phase == 1) {
-      const uint8_t k = classify (c);
-      if (k <= 3) out[n_out++] = k;
-      else if (k == CODE_BREAK || k == CODE_GT) out[n_out++] = CODE_BREAK;   // '>' is an ordinary character in FastQ
-    }
-  }
+  const int n_mine = base >= n ? 0 : (n - base < (uint64_t) FA_BYTES ? (int) (n - base) : FA_BYTES);
+  const uint32_t n_out = (uint32_t) walk_fastq (ch, n_mine, line, at_line_start, out, &bad);
   if (bad) atomicOr (malformed, 1u);
   const uint32_t at = block_exclusive_sum (n_out, s_sum, &total);
   if (MODE == MODE_COUNT) {
@@ -293,24 +232,9 @@ fasta_words_kernel (const uint8_t *__restrict__ codes, uint64_t n_codes, unsigne
 {
   __shared__ uint32_t s_sum[FA_NT / 32];
   const uint64_t j0 = (uint64_t) blockIdx.x * FA_CHUNK + (uint64_t) threadIdx.x * FA_BYTES;
-  const uint64_t mask = k >= 32 ? ~0ull : (1ull << (2 * k)) - 1;
-  const unsigned top = 2 * (k - 1);
-  uint64_t fw = 0, rc = 0;
-  unsigned have = 0;
   uint64_t out[FA_BYTES];
   uint32_t n_out = 0;
-  if (j0 < n_codes) {
-    const uint64_t start = j0 >= k - 1 ? j0 - (k - 1) : 0;
-    const uint64_t stop = j0 + FA_BYTES < n_codes ? j0 + FA_BYTES : n_codes;
-    for (uint64_t j = start; j < stop; j++) {
-      const uint8_t c = codes[j];
-      if (c > 3) { have = 0; fw = rc = 0; continue; }
-      fw = ((fw << 2) | c) & mask;
-      rc = (rc >> 2) | ((uint64_t) (3u - c) << top);
-      if (have < k) have++;
-      if (have == k && j >= j0) out[n_out++] = fw < rc ? fw : rc;
-    }
-  }
+  if (j0 < n_codes) n_out = (uint32_t) window_words (codes, j0, j0 + FA_BYTES < n_codes ? j0 + FA_BYTES : n_codes, k, out);
   uint32_t total;
   const uint32_t at = block_exclusive_sum (n_out, s_sum, &total);
   if (MODE == MODE_COUNT) {
