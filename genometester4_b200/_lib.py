@@ -23,6 +23,10 @@ def listmaker_cli_path() -> Path:
     return PKG / "gt4gpu-listmaker"
 
 
+def query_cli_path() -> Path:
+    return PKG / "gt4gpu-query"
+
+
 def build(verbose: bool = False) -> Path:
     """Compile the CUDA library and the CLI for sm_100a, in-tree (nvcc cross-compiles without a GPU)."""
     subprocess.run(["make", "-C", str(CSRC), "all"], check=True,
@@ -71,6 +75,7 @@ SIGNATURES = {
     "gt4gpu_intersect_multi": (_I, [C.POINTER(_P), C.c_uint, _U32, _I, _U32, _I, C.POINTER(CResult)]),
     "gt4gpu_write_union": (_I, [C.POINTER(_P), C.c_uint, _U32, _I, C.POINTER(Header)]),
     "gt4gpu_union_matrix": (_I, [C.POINTER(_P), C.c_uint, _I, _P, _P, _U64, C.POINTER(_U64)]),
+    "gt4gpu_list_to_host_soa": (_I, [_P, _P, _P]),
     "gt4gpu_lookup": (_I, [_P, _P, _U64, _I, _I, _P, _P]),
     "gt4gpu_sequence_words": (_I, [_P, _U64, _U32, _P, _U64, C.POINTER(_U64)]),
     "gt4gpu_fasta_words_device": (_I, [_P, _U64, _U32, C.POINTER(_P), C.POINTER(_U64)]),

@@ -877,6 +877,18 @@ void gt4gpu_list_close (gt4gpu_list *list)
   free (list);
 }
 
+int gt4gpu_list_to_host_soa (const gt4gpu_list *list, uint64_t *words, uint32_t *counts)
+{
+  if (!list || (list->n_words && (!words || !counts))) return fail (GT4GPU_ERR_ARG, "null argument");
+  int rc = ensure_ready ();
+  if (rc) return rc;
+  if (!list->n_words) return 0;
+  CU (cudaMemcpyAsync (words, list->words, list->n_words * sizeof (uint64_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+  CU (cudaMemcpyAsync (counts, list->counts, list->n_words * sizeof (uint32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+  CU (cudaStreamSynchronize (g_ctx.stream));
+  return 0;
+}
+
 uint64_t gt4gpu_list_n_words (const gt4gpu_list *l) { return l ? l->n_words : 0; }
 uint32_t gt4gpu_list_word_length (const gt4gpu_list *l) { return l ? l->word_length : 0; }
 uint64_t gt4gpu_list_sum_counts (const gt4gpu_list *l) { return l ? l->sum_counts : 0; }

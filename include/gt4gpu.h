@@ -144,6 +144,9 @@ uint64_t gt4gpu_list_n_words (const gt4gpu_list *list);
 uint32_t gt4gpu_list_word_length (const gt4gpu_list *list);
 uint64_t gt4gpu_list_sum_counts (const gt4gpu_list *list);   /* header total_count (0 if built from arrays) */
 const uint64_t *gt4gpu_list_device_words (const gt4gpu_list *list);
+/* Copies the list's words and counts back to host arrays of gt4gpu_list_n_words entries (what walking the container
+ * with get_first_word / get_next_word, src/word-list-sorted.c:59-78, would visit). */
+int gt4gpu_list_to_host_soa (const gt4gpu_list *list, uint64_t *words, uint32_t *counts);
 const uint32_t *gt4gpu_list_device_counts (const gt4gpu_list *list);
 
 /* ---- merges --------------------------------------------------------------------------- */

@@ -62,6 +62,16 @@ def main():
         O.write_list(OUT / f"sub_{k}.list", sub, sub_counts, k)
         r = O.run_ref("glistquery", [f"main_{k}.list", "-l", f"sub_{k}.list"], cwd=OUT, check=True, timeout=20)
         (OUT / f"zipper_{k}.out").write_bytes(r.stdout)
+        # whole-tool outputs for the gt4gpu-query CLI: dump, count matrices, multi-list search, frequency window, -stat
+        for name, args in ((f"dump_{k}.out", [f"main_{k}.list"]),
+                           (f"matrix_{k}.out", [f"main_{k}.list", f"sub_{k}.list"]),
+                           (f"matrix_isunion_{k}.out", [f"main_{k}.list", f"sub_{k}.list", "--is_union", "--header"]),
+                           (f"multi_{k}.out", [f"main_{k}.list", f"sub_{k}.list", "-l", f"sub_{k}.list"]),
+                           (f"lookup_minmax_{k}.out", [f"main_{k}.list", "-f", f"queries_{k}.txt", "-min", "100", "-max", "500"]),
+                           (f"stat_{k}.out", [f"main_{k}.list", "-stat"])):
+            if k in (5, 16):
+                r = O.run_ref("glistquery", args, cwd=OUT, check=True, timeout=20)
+                (OUT / name).write_bytes(r.stdout)
         cases.append({"k": k, "n_main": int(words.size), "n_queries": int(q.size), "n_sub": int(sub.size)})
     (OUT / "query_golden.json").write_text(json.dumps({"tool": "glistquery 4.2.16 (oracle/_ref)", "cases": cases}, indent=1) + "\n")
     print("written", OUT)

@@ -142,3 +142,42 @@ def test_entry_points_are_reentrant(g, oracle):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_query_cli_against_glistquery_golden():
+    """gt4gpu-query prints byte for byte what the unmodified glistquery printed (committed outputs): dump, count
+    matrices, exact lookups from a query file / a single word / a FastA file, frequency window, zipper, multi-list search."""
+    import subprocess
+    from genometester4_b200 import _lib
+    cli = str(_lib.query_cli_path())
+
+    def run(*args):
+        r = subprocess.run([cli, *args], cwd=GOLD_DIR, capture_output=True)
+        assert r.returncode == 0, (args, r.stderr)
+        return r.stdout
+
+    for k in (5, 16):
+        assert run(f"main_{k}.list") == (GOLD_DIR / f"dump_{k}.out").read_bytes()
+        assert run(f"main_{k}.list", f"sub_{k}.list") == (GOLD_DIR / f"matrix_{k}.out").read_bytes()
+        assert run(f"main_{k}.list", f"sub_{k}.list", "--is_union", "--header") == (GOLD_DIR / f"matrix_isunion_{k}.out").read_bytes()
+        assert run(f"main_{k}.list", f"sub_{k}.list", "-l", f"sub_{k}.list") == (GOLD_DIR / f"multi_{k}.out").read_bytes()
+        assert run(f"main_{k}.list", "-f", f"queries_{k}.txt", "-min", "100", "-max", "500") == (GOLD_DIR / f"lookup_minmax_{k}.out").read_bytes()
+    for case in GOLD["cases"]:
+        k = case["k"]
+        want = (GOLD_DIR / f"lookup_{k}.out").read_bytes()
+        assert run(f"main_{k}.list", "-f", f"queries_{k}.txt") == want
+        assert run(f"main_{k}.list", "-l", f"sub_{k}.list") == (GOLD_DIR / f"zipper_{k}.out").read_bytes()
+        first = (GOLD_DIR / f"queries_{k}.txt").read_text().split()[0]
+        assert run(f"main_{k}.list", "-q", first) == want.split(b"\n")[0] + b"\n"
+    # -s: every k-mer of a FastA file, in file order (canonical forms, absent ones with count 0)
+    import tempfile
+    k = 5
+    seq = "ACGTTGCAAGGCTTNACGTACGTTTGACCA"
+    with tempfile.NamedTemporaryFile("w", suffix=".fa", delete=False) as f:
+        f.write(">s\n" + seq + "\n")
+    words = [seq[i:i + k] for i in range(len(seq) - k + 1) if "N" not in seq[i:i + k]]
+    from oracle import oracle as O
+    main = O.read_list(GOLD_DIR / f"main_{k}.list")
+    q = np.array([sum("ACGT".index(c) << (2 * (k - 1 - j)) for j, c in enumerate(w)) for w in words], dtype=np.uint64)
+    cw, cc = O.lookup(main, q)
+    assert run(f"main_{k}.list", "-s", f.name) == lines(O, cw, cc, k)

@@ -60,3 +60,52 @@ def test_oracle_lookup_vs_live_glistquery(oracle, tmp_path):
     cw, cc = oracle.lookup(oracle.SList(words, counts, k), q)
     assert lines(oracle, cw, cc, k) == r.stdout
     assert (cc > 0).sum() > 20 and (cc == 0).sum() > 20
+
+
+# ---- gt4gpu-query: flag grammar, validation and -stat (no device needed on these paths)
+
+QUERY_CLI_CASES = [
+    [],
+    ["-v"], ["--version"], ["-h"],
+    ["-q", "ACGTA"],
+    ["main_5.list", "--bogus"],
+    ["nosuch.list"],
+    ["queries_5.txt"],
+    ["main_5.list", "main_16.list"],
+    ["main_5.list", "-stat"], ["main_5.list", "sub_5.list", "--stats"],
+    ["main_5.list", "-min", "x"], ["main_5.list", "-max", "3y"],
+    ["main_5.list", "sub_5.list", "-q", "ACGTA"],
+    ["main_5.list", "-l", "sub_16.list"],
+    ["main_5.list", "-mm"], ["main_5.list", "-p", "40"],
+]
+
+
+@pytest.mark.parametrize("args", QUERY_CLI_CASES, ids=lambda a: " ".join(a)[:40] or "noargs")
+def test_query_cli_validation_matches_reference(args, oracle):
+    import subprocess
+    from genometester4_b200 import _lib
+    cli = _lib.query_cli_path()
+    assert cli.exists(), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    if oracle.ref_binary("glistquery") is None:
+        pytest.skip("oracle/_ref not built")
+    mine = subprocess.run([str(cli), *args], cwd=GOLD_DIR, capture_output=True)
+    ref = oracle.run_ref("glistquery", args, cwd=GOLD_DIR, timeout=20)
+    assert mine.returncode == ref.returncode, (mine.stderr, ref.stderr)
+    assert mine.stdout == ref.stdout
+    if args == ["queries_5.txt"]:
+        # the reference goes on after its diagnostic (an assertion with its own source path)
+        assert mine.stderr.split(b"\n")[0] == ref.stderr.split(b"\n")[0]
+    else:
+        assert mine.stderr == ref.stderr
+
+
+def test_query_cli_static_expectations():
+    import subprocess
+    from genometester4_b200 import _lib
+    cli = _lib.query_cli_path()
+    r = subprocess.run([str(cli), "-v"], capture_output=True)
+    assert r.returncode == 0 and r.stdout == b"glistquery version 4.2.16 (stable)\n"
+    r = subprocess.run([str(cli), "main_16.list", "-stat"], cwd=GOLD_DIR, capture_output=True)
+    assert r.returncode == 0 and r.stdout == (GOLD_DIR / "stat_16.out").read_bytes()
+    r = subprocess.run([str(cli), "main_16.list", "-q", "ACGT", "-mm", "1"], cwd=GOLD_DIR, capture_output=True)
+    assert r.returncode == 1 and b"not supported" in r.stderr
