@@ -77,3 +77,15 @@ def test_index_header_is_readable_without_a_device():
     idx = ROOT / "tests" / "golden" / "index" / "x_16.index"
     assert _lib.load().gt4gpu_list_read_header(str(idx).encode(), 0, C.byref(h)) == 0
     assert bytes(h)[:4] == b"I4TG" and (h.word_length, h.word_bytes, h.count_bytes) == (16, 8, 8) and h.n_words > 2000
+
+
+def test_header_compiles_as_c99_and_cxx(tmp_path):
+    """include/gt4gpu.h is the drop-in boundary: it must be consumable by a plain C99 host (the reference is C) and by C++."""
+    import subprocess
+    root = Path(__file__).resolve().parent.parent
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "gt4gpu.h"\nint main (void) { gt4gpu_header h; gt4gpu_result r; (void) h; (void) r; '
+                   'return sizeof (gt4gpu_header) == 48 ? 0 : 1; }\n')
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++17")):
+        lang = ["-x", "c++"] if cc == "g++" else []
+        subprocess.run([cc, std, "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{root / 'include'}", "-fsyntax-only", *lang, str(src)], check=True)
