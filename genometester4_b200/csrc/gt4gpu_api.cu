@@ -69,6 +69,7 @@ struct Context {
   int stream_consumers = 512;   // consumer threads per CTA of the single-output kernel (setop2_stream_kernel)
   int stream_items = 9;         // its merged items per thread
   int use_stream = 1;           // 0: run single-output merges through setop2_tile_kernel too
+  int use_kway = 1;             // 0: N-list calls go through the tree / chain of two-list merges
   int sm_count = 0;
 };
 Context g_ctx;
@@ -658,6 +659,197 @@ int union_tree (const std::vector<DevList> &leaves, int rule, uint32_t cutoff, u
   return 0;
 }
 
+
+// ---- single-pass N-list union / intersection (gt4gpu_kway_kernel.cu) ----------------------------------------------
+
+enum { KWAY_UNION = 0, KWAY_ISECT = 1 };
+
+// One pass over 1..KWAY_MAX_LISTS device lists.  *fallback is set (and nothing else returned) when the pass does not
+// apply: list arrays that are not 16-byte aligned, or a tile beyond the capacity the sampling bound covers.
+int kway_pass (const std::vector<DevList> &lists, int op, int rule, uint32_t cutoff, uint32_t ov, bool final_pass, bool countonly,
+               MergeOut *out, bool *fallback)
+{
+  *fallback = false;
+  const int n_lists = (int) lists.size ();
+  if (n_lists < 1 || n_lists > KWAY_MAX_LISTS) return fail (GT4GPU_ERR_ARG, "kway_pass: %d lists", n_lists);
+  uint64_t total = 0, smallest = UINT64_MAX, n_samples = 0;
+  KwayArgs args;
+  memset (&args, 0, sizeof (args));
+  for (int j = 0; j < n_lists; j++) {
+    const DevList &l = lists[j];
+    if (l.n && ((((uintptr_t) l.words) | ((uintptr_t) l.counts)) & 15u)) { *fallback = true; return 0; }
+    args.words[j] = l.words; args.counts[j] = l.counts; args.n[j] = l.n;
+    args.sample_off[j] = n_samples;
+    n_samples += l.n / KWAY_SAMPLE;
+    total += l.n;
+    smallest = std::min (smallest, l.n);
+  }
+  const int nl = n_lists <= 4 ? 4 : 8;
+  const uint64_t every = (uint64_t) (KWAY_TILE_CAP / KWAY_SAMPLE - n_lists - 2);       // samples per tile
+  const uint64_t n_tiles = n_samples ? (n_samples - 1) / every + 1 : 1;
+  cudaStream_t st = g_ctx.stream;
+
+  out->n = out->sum = 0;
+  const uint64_t worst = (op == KWAY_ISECT) ? smallest : total;
+  const bool own_out = !countonly && !out->caller;
+  if (own_out) {
+    out->capacity = worst;
+    out->words = nullptr; out->counts = nullptr;
+    int rc = dev_alloc ((void **) &out->words, worst * sizeof (uint64_t));
+    if (!rc) rc = dev_alloc ((void **) &out->counts, worst * sizeof (uint32_t));
+    if (rc) { free_out (*out); return rc; }
+  }
+  if (total == 0 || (op == KWAY_ISECT && smallest == 0)) return 0;
+
+  // scratch: [CallHeader | descriptors | cuts | bounds | samples | sort buffer | sort scratch]
+  const size_t hdr_bytes = (sizeof (CallHeader) + 255) & ~(size_t) 255;
+  const size_t desc_bytes = (countonly ? 0 : (size_t) n_tiles * sizeof (uint64_t) + 255) & ~(size_t) 255;
+  const size_t cuts_bytes = ((size_t) (n_tiles + 1) * nl * sizeof (uint64_t) + 255) & ~(size_t) 255;
+  const size_t bounds_bytes = ((size_t) (n_tiles + 1) * sizeof (uint64_t) + 255) & ~(size_t) 255;
+  const size_t smp_bytes = ((size_t) n_samples * sizeof (uint64_t) + 255) & ~(size_t) 255;
+  const size_t sort_bytes = n_samples ? sort_scratch_bytes (n_samples) : 0;
+  unsigned char *ws = nullptr;
+  int rc = dev_alloc ((void **) &ws, hdr_bytes + desc_bytes + cuts_bytes + bounds_bytes + 2 * smp_bytes + sort_bytes);
+  if (rc) { if (own_out) free_out (*out); return rc; }
+  struct ScratchGuard {
+    unsigned char *&p;
+    ~ScratchGuard () { if (p) { dev_free (p); p = nullptr; } }
+  } guard{ws};
+  auto bail = [&] (cudaError_t e, const char *what) {
+    if (own_out) free_out (*out);
+    return fail (GT4GPU_ERR_CUDA, "%s: %s", what, cudaGetErrorString (e));
+  };
+  cudaError_t e = cudaMemsetAsync (ws, 0, hdr_bytes + desc_bytes, st);
+  if (e != cudaSuccess) return bail (e, "kway scratch");
+  uint64_t *cuts = reinterpret_cast<uint64_t *> (ws + hdr_bytes + desc_bytes);
+  uint64_t *bounds = reinterpret_cast<uint64_t *> (ws + hdr_bytes + desc_bytes + cuts_bytes);
+  uint64_t *smp = reinterpret_cast<uint64_t *> (ws + hdr_bytes + desc_bytes + cuts_bytes + bounds_bytes);
+  uint64_t *smp_alt = reinterpret_cast<uint64_t *> (ws + hdr_bytes + desc_bytes + cuts_bytes + bounds_bytes + smp_bytes);
+  unsigned char *sort_ws = ws + hdr_bytes + desc_bytes + cuts_bytes + bounds_bytes + 2 * smp_bytes;
+
+  args.n_lists = n_lists;
+  args.n_real = n_lists;
+  args.cuts = cuts;
+  args.bounds = bounds;
+  args.n_tiles = n_tiles;
+  args.out_words = out->words;
+  args.out_counts = out->counts;
+  args.out_capacity = countonly ? 0 : out->capacity;
+  args.hdr = reinterpret_cast<CallHeader *> (ws);
+  args.desc = reinterpret_cast<uint64_t *> (ws + hdr_bytes);
+  args.op = op;
+  args.rule = rule;
+  args.cutoff = cutoff;
+  args.count_override = ov;
+  args.final_pass = final_pass ? 1 : 0;
+  args.debug = debug_flags ();
+
+  for (int i = 0; i < 3; i++) if (!tl_ev[i]) { e = cudaEventCreate (&tl_ev[i]); if (e != cudaSuccess) return bail (e, "cudaEventCreate"); }
+  cudaEventRecord (tl_ev[0], st);
+  uint64_t *sorted = smp;
+  uint32_t n_launches = 2;
+  if (n_samples) {
+    e = launch_kway_samples (args, n_samples, smp, st);
+    // all 64 key bits: the boundaries must be in key order whatever the lists' word length says
+    if (e == cudaSuccess) e = launch_radix_sort (smp, smp, smp_alt, n_samples, SORT_MAX_PASSES, sort_ws, g_ctx.sm_count, &sorted, st);
+    if (e != cudaSuccess) return bail (e, "kway samples");
+    n_launches += 3 + SORT_MAX_PASSES;
+  }
+  e = launch_kway_cuts (args, sorted, every, nl, cuts, bounds, st);
+  if (e != cudaSuccess) return bail (e, "kway cuts");
+  cudaEventRecord (tl_ev[1], st);
+  e = launch_kway_tiles (args, nl, countonly, g_ctx.sm_count, st);
+  if (e != cudaSuccess) return bail (e, "kway tiles");
+  cudaEventRecord (tl_ev[2], st);
+  CallHeader h;
+  e = cudaMemcpyAsync (&h, ws, sizeof (h), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize (st);
+  if (e != cudaSuccess) return bail (e, "kway pass");
+  float ms = 0.f;
+  cudaEventElapsedTime (&ms, tl_ev[0], tl_ev[1]);
+  tl_ms_partition += ms;
+  cudaEventElapsedTime (&ms, tl_ev[1], tl_ev[2]);
+  tl_ms_merge += ms;
+  tl_launches += n_launches;
+  if (h.overflow) {
+    if (own_out) free_out (*out);
+    if (h.overflow == 3u) { *fallback = true; return 0; }
+    if (h.overflow == 2u) return fail (GT4GPU_ERR_ARG, "input lists are not strictly ascending (the merge result is undefined)");
+    return fail (GT4GPU_ERR_CAPACITY, "output buffer too small for the merge result");
+  }
+  for (int k = 0; k < TOTAL_SLOTS; k++) {
+    out->n += h.totals[0][k][0];
+    out->sum += h.totals[0][k][1];
+  }
+  return 0;
+}
+
+// N-list union through single passes over groups of up to KWAY_MAX_LISTS lists (add / max / number are associative and
+// commutative, so any grouping reproduces union_multi's fold); inner passes keep every word, the last one applies the
+// cut-off.  *fallback: the caller runs the tree of two-list merges instead.
+int union_kway (const std::vector<DevList> &leaves, int rule, uint32_t cutoff, uint32_t ov, bool countonly, MergeOut *root, bool *fallback)
+{
+  std::vector<TreeNode> level;
+  for (const DevList &l : leaves) level.push_back (TreeNode{l, MergeOut (), false});
+  auto release_all = [] (std::vector<TreeNode> &v) { for (auto &n : v) if (n.is_owned) { free_out (n.owned); n.is_owned = false; } };
+  while (level.size () > (size_t) KWAY_MAX_LISTS) {
+    const size_t n_groups = (level.size () + KWAY_MAX_LISTS - 1) / KWAY_MAX_LISTS;
+    std::vector<TreeNode> next;
+    size_t at = 0;
+    for (size_t g = 0; g < n_groups; g++) {
+      const size_t take = (level.size () - at + (n_groups - g) - 1) / (n_groups - g);      // near-equal groups
+      if (take == 1) {
+        next.push_back (level[at]);
+        level[at].is_owned = false;
+        at += 1;
+        continue;
+      }
+      std::vector<DevList> group;
+      for (size_t k = 0; k < take; k++) group.push_back (level[at + k].list);
+      MergeOut part;
+      int rc = kway_pass (group, KWAY_UNION, rule, cutoff, ov, false, false, &part, fallback);
+      if (rc || *fallback) { release_all (level); release_all (next); return rc; }
+      for (size_t k = 0; k < take; k++) if (level[at + k].is_owned) { free_out (level[at + k].owned); level[at + k].is_owned = false; }
+      next.push_back (TreeNode{DevList{part.words, part.counts, part.n}, part, true});
+      at += take;
+    }
+    level.swap (next);
+  }
+  std::vector<DevList> last;
+  for (auto &n : level) last.push_back (n.list);
+  MergeOut out;
+  if (root->caller) out = *root;
+  int rc = kway_pass (last, KWAY_UNION, rule, cutoff, ov, true, countonly, &out, fallback);
+  release_all (level);
+  if (rc || *fallback) return rc;
+  *root = out;
+  return 0;
+}
+
+// N-list intersection: the reference folds the counts list by list (glistcompare.c:668-677) and rule min's "!freq ||"
+// guard makes that fold order-dependent, so many lists run as a chain of passes whose first list is the running result.
+int intersect_kway (const std::vector<DevList> &lists, int rule, uint32_t cutoff, uint32_t ov, bool countonly, MergeOut *root, bool *fallback)
+{
+  MergeOut acc;
+  bool have_acc = false;
+  size_t at = 0;
+  while (at < lists.size ()) {
+    std::vector<DevList> group;
+    if (have_acc) group.push_back (DevList{acc.words, acc.counts, acc.n});
+    while (at < lists.size () && group.size () < (size_t) KWAY_MAX_LISTS) group.push_back (lists[at++]);
+    const bool last = at == lists.size ();
+    MergeOut out;
+    if (last && root->caller) out = *root;
+    int rc = kway_pass (group, KWAY_ISECT, rule, cutoff, ov, last, last && countonly, &out, fallback);
+    if (have_acc) free_out (acc);
+    if (rc || *fallback) return rc;
+    acc = out;
+    have_acc = true;
+  }
+  *root = acc;
+  return 0;
+}
+
 }  // namespace
 
 // ============================================================================ ABI
@@ -706,6 +898,8 @@ int gt4gpu_init (int device)
   }
   env = getenv ("GT4GPU_USE_STREAM_KERNEL");
   if (env) g_ctx.use_stream = atoi (env) != 0;
+  env = getenv ("GT4GPU_USE_KWAY");
+  if (env) g_ctx.use_kway = atoi (env) != 0;
   env = getenv ("GT4GPU_TILE");   // multi-output kernel, e.g. GT4GPU_TILE=256x11
   if (env) {
     int nt = 0, vt = 0;
@@ -762,6 +956,10 @@ int gt4gpu_set_option (const char *name, int value)
   if (!strcmp (name, "stream_consumers")) {
     if (!stream_shape_supported (value, g_ctx.stream_items)) return fail (GT4GPU_ERR_ARG, "stream shape %dx%d is not supported", value, g_ctx.stream_items);
     g_ctx.stream_consumers = value;
+    return 0;
+  }
+  if (!strcmp (name, "use_kway")) {            // 0: N-list calls run as a tree / chain of two-list merges
+    g_ctx.use_kway = value != 0;
     return 0;
   }
   if (!strcmp (name, "use_stream_kernel")) {
@@ -969,7 +1167,13 @@ int gt4gpu_union_multi (const gt4gpu_list *const *lists, unsigned n_lists, uint3
     root.counts = out->counts;
     root.capacity = out->capacity;
   }
-  rc = union_tree (level, rule, cutoff, count_override, countonly != 0, &root);
+  bool fallback = true;
+  if (g_ctx.use_kway && level.size () >= 3) {
+    rc = union_kway (level, rule, cutoff, count_override, countonly != 0, &root, &fallback);
+    if (rc) return rc;
+    if (fallback) reset_timing ();
+  }
+  if (fallback) rc = union_tree (level, rule, cutoff, count_override, countonly != 0, &root);
   if (rc) return rc;
   fill_result (out, root, k, countonly != 0);
   return 0;
@@ -1013,6 +1217,20 @@ int gt4gpu_intersect_multi (const gt4gpu_list *const *lists, unsigned n_lists, u
     if (rc) { free_out (mo[0]); return rc; }
     fill_result (out, mo[0], k, countonly != 0);
     return 0;
+  }
+  if (g_ctx.use_kway && n_lists >= 3) {
+    std::vector<DevList> all;
+    for (unsigned j = 0; j < n_lists; j++) all.push_back (DevList{lists[j]->words, lists[j]->counts, lists[j]->n_words});
+    MergeOut root;
+    if (caller) { root.caller = true; root.words = out->words; root.counts = out->counts; root.capacity = out->capacity; }
+    bool fallback = false;
+    rc = intersect_kway (all, rule, cutoff, count_override, countonly != 0, &root, &fallback);
+    if (rc) return rc;
+    if (!fallback) {
+      fill_result (out, root, k, countonly != 0);
+      return 0;
+    }
+    reset_timing ();
   }
   // left chain ((L0 ^ L1) ^ L2) ...: exactly the reference's in-order fold (:668-677), including
   // the "!freq ||" guard of rule min; only the last link applies the cut-off (:682)

@@ -65,6 +65,42 @@ cudaError_t launch_setop2 (const TileArgs &args, TileShape shape, int n_streams,
 bool stream_shape_supported (int consumers, int items);
 cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items, bool count_only, int sm_count, cudaStream_t st);
 
+// ---- single-pass N-list union / intersection (gt4gpu_kway_kernel.cu)
+static constexpr int KWAY_MAX_LISTS = 8;        // lists per pass (their heads live in registers); more lists go through several passes
+static constexpr int KWAY_SAMPLE = 128;         // every KWAY_SAMPLE-th word of every list is a boundary candidate
+static constexpr int KWAY_TILE_CAP = 4096;      // records a tile can hold
+static constexpr int KWAY_CONSUMERS = 256;
+enum KwayMode : int { KWAY_MODE_GENERIC = 0, KWAY_MODE_U_ADD = 1, KWAY_MODE_I_MIN = 2 };
+
+struct KwayArgs {
+  const uint64_t *words[KWAY_MAX_LISTS];        // 16-byte aligned arrays; unused entries: n = 0
+  const uint32_t *counts[KWAY_MAX_LISTS];
+  uint64_t n[KWAY_MAX_LISTS];
+  uint64_t sample_off[KWAY_MAX_LISTS];          // position of list j's samples in the sample array
+  int n_lists;                 // lists taking part
+  int n_real;                  // an intersection keeps a word found in n_real lists
+  const uint64_t *cuts;        // [n_tiles + 1][NL]: first record of every tile in every list
+  const uint64_t *bounds;      // [n_tiles + 1]: key range of tile t = [bounds[t], bounds[t + 1]]
+  uint64_t n_tiles;
+  uint64_t *out_words;
+  uint32_t *out_counts;
+  uint64_t out_capacity;
+  CallHeader *hdr;
+  uint64_t *desc;
+  int op;                      // 0 union, 1 intersection
+  int rule;                    // RULE_ADD / MAX / MIN / NUMBER
+  uint32_t cutoff;
+  uint32_t count_override;
+  int final_pass;              // apply the cut-off (inner passes of a many-list call keep everything)
+  int debug;
+};
+
+int kway_select_mode (int op, int rule);
+cudaError_t launch_kway_samples (const KwayArgs &args, uint64_t n_samples, uint64_t *samples, cudaStream_t st);
+// every-th sorted sample is a boundary; nl = 4 or 8 (the kernel variant: lists are padded to it)
+cudaError_t launch_kway_cuts (const KwayArgs &args, const uint64_t *sorted_samples, uint64_t every, int nl, uint64_t *cuts, uint64_t *bounds, cudaStream_t st);
+cudaError_t launch_kway_tiles (const KwayArgs &args, int nl, bool count_only, int sm_count, cudaStream_t st);
+
 cudaError_t launch_deinterleave (const void *records, uint64_t n, uint64_t *words, uint32_t *counts, cudaStream_t st);
 cudaError_t launch_interleave (const uint64_t *words, const uint32_t *counts, uint64_t n, void *records, cudaStream_t st);
 

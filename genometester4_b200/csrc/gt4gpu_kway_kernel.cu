@@ -1,0 +1,622 @@
+// gt4gpu_kway_kernel.cu -- single-pass N-list union / intersection (N <= 8 per pass).
+//
+// Replaces the loops of union_multi / intersect_multi (/root/reference/src/glistcompare.c:545-591, :647-705) and of
+// gt4_write_union (src/set-operations.c:77-116): every list is read ONCE and the result written once, instead of a
+// tree of two-list passes with materialised intermediates.
+//
+// Decomposition (all by KEY, so equal words of different lists always meet in one place):
+//
+//   kway_sample_kernel    every KW_SAMPLE-th word of every list -> one array; it is radix-sorted with the list-building
+//                         sort (gt4gpu_sort_kernel.cu)
+//   kway_cuts_kernel      every m-th sorted sample is a tile boundary key; one lower-bound search per (boundary, list)
+//                         gives the tile's slice of every list.  A tile holds at most (m + 2 N) * KW_SAMPLE records.
+//   kway_tile_kernel      persistent, warp-specialised, mbarrier pipeline like setop2_stream_kernel:
+//       producer warp     claims tiles by ticket, stages the N key slices + N count slices with 1-D TMA bulk copies
+//                         (one lane per slice; slices are packed so that keys and counts share ONE index space)
+//       consumers         (1) cut the tile's key range [lo, hi] into one bucket per consumer thread -- bucket =
+//                         (key - lo) * NB / (hi - lo + 1), one multiply per record, no search -- and record in a small
+//                         table where every bucket starts in every slice; (2) every thread merges its bucket with the
+//                         N slice heads in registers: the smallest head is the next distinct word, all lists holding it
+//                         advance together and their counts are folded by the rule (add / max / min with the
+//                         reference's "!freq ||" guard / number); survivors of the cut-off go to a scratch buffer at
+//                         the thread's input offset; (3) block scan of the survivor counts, hand the tile total to the
+//                         look-back warp, compact the survivors to the front of the stage buffer
+//       look-back warps   one per stage: decoupled look-back for the tile's global output offset
+//       store warps       coalesced copy of the compacted tile to the output arrays, stage back to the producer
+//
+// The bucket split is exact in keys and approximate in load: it assumes the words of a tile (a key range only a few
+// thousand words wide) are spread about evenly; a skewed tile is still merged correctly, by fewer threads.
+//
+// HBM-bound integer work: no tensor cores.  Algorithmic traffic 12 B per input record + 12 B per output record.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gt4gpu_device.cuh"
+#include "gt4gpu_internal.h"
+
+namespace gt4gpu {
+
+namespace {
+
+using namespace dev;
+
+constexpr int KW_STORE_WARPS = 2;
+constexpr uint64_t KW_TILE_END = ~0ull;
+constexpr int KW_LB_W = 4;
+
+template <int NL, int NC, int S>
+struct KwayCfg {
+  static constexpr int NWARPS = NC / 32;
+  static constexpr int PRODUCER_WARP = NWARPS;
+  static constexpr int LOOKBACK_WARP0 = NWARPS + 1;
+  static constexpr int STORE_WARP0 = LOOKBACK_WARP0 + S;
+  static constexpr int NTHREADS = NC + 32 + 32 * S + 32 * KW_STORE_WARPS;
+  static constexpr int NB = NC;                                  // one bucket per consumer thread
+  // every slice starts on a 4-slot boundary plus its count phase (0..3) and is padded to a multiple of 4 slots
+  static constexpr int SLOTS = KWAY_TILE_CAP + 8 * NL + 8;
+  static constexpr size_t STAGE_BYTES = (size_t) SLOTS * 12;
+  static constexpr size_t SPARSE_BYTES = (size_t) KWAY_TILE_CAP * 12;
+  static constexpr int TAB_STRIDE = NB + 2;
+  static constexpr size_t TAB_BYTES = ((size_t) NL * TAB_STRIDE * 2 + 15) & ~(size_t) 15;
+  static constexpr size_t SMEM_BYTES = S * STAGE_BYTES + SPARSE_BYTES + TAB_BYTES;
+  static_assert (SLOTS % 4 == 0, "the count region must start 16-byte aligned");
+  static_assert (SLOTS < 65536, "slot indices are kept as u16");
+};
+
+template <int NL>
+struct KwMeta {
+  uint64_t tile;      // KW_TILE_END: no more work
+  uint64_t lo;        // smallest key the tile can hold
+  uint64_t hi;        // largest key the tile can hold
+  uint64_t mult;      // bucket = (((key - lo) >> sh) * mult) >> 32
+  int sh;
+  int n_total;
+  uint16_t idx0[NL];  // slot of the slice's first record (keys and counts share the index space)
+  uint16_t n[NL];
+};
+
+struct KwMailbox {
+  uint64_t tile;
+  uint64_t base;
+  int cnt;
+};
+
+__device__ __forceinline__ unsigned kw_bucket (uint64_t key, uint64_t lo, int sh, uint64_t mult, unsigned nb)
+{
+  const uint64_t d = ((key - lo) >> sh) & 0xffffffffull;
+  const unsigned b = (unsigned) ((d * mult) >> 32);
+  return b < nb ? b : nb - 1;
+}
+
+// fold of one more list's count into the running count of a word
+template <int MODE>
+__device__ __forceinline__ uint32_t kw_fold (uint32_t f, uint32_t c, bool first, int rule)
+{
+  if (MODE == KWAY_MODE_U_ADD) return f + c;
+  if (MODE == KWAY_MODE_I_MIN) return (first || f == 0u || c < f) ? c : f;       // glistcompare.c:668-671 ("!freq ||")
+  switch (rule) {
+  case RULE_ADD: return f + c;
+  case RULE_MAX: return (first || c > f) ? c : f;
+  case RULE_MIN: return (first || f == 0u || c < f) ? c : f;
+  default:       return f;          // RULE_NUMBER: the override is set after the fold
+  }
+}
+
+template <int NL, int NC, int S, int MODE, bool COUNT_ONLY>
+__global__ void __launch_bounds__ (KwayCfg<NL, NC, S>::NTHREADS, 1)
+kway_tile_kernel (const KwayArgs args)
+{
+  using Cfg = KwayCfg<NL, NC, S>;
+  constexpr int NWARPS = Cfg::NWARPS;
+  constexpr int NB = Cfg::NB;
+  constexpr int SLOTS = Cfg::SLOTS;
+  constexpr int TS = Cfg::TAB_STRIDE;
+
+  extern __shared__ __align__ (128) unsigned char smem_raw[];
+  __shared__ __align__ (8) uint64_t bar_full[S];
+  __shared__ __align__ (8) uint64_t bar_comp[S];
+  __shared__ __align__ (8) uint64_t bar_agg[S];
+  __shared__ __align__ (8) uint64_t bar_base[S];
+  __shared__ __align__ (8) uint64_t bar_empty[S];
+  __shared__ KwMeta<NL> s_meta[S];
+  __shared__ KwMailbox s_mail[S];
+  __shared__ int s_wcnt[2][NWARPS];
+  __shared__ int s_bad[3];
+  __shared__ volatile unsigned int s_n_iter;
+  __shared__ unsigned long long s_red[2][NWARPS];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      mbar_init (&bar_full[s], 1);
+      mbar_init (&bar_comp[s], NWARPS);
+      mbar_init (&bar_agg[s], 1);
+      mbar_init (&bar_base[s], 1);
+      mbar_init (&bar_empty[s], COUNT_ONLY ? NWARPS : KW_STORE_WARPS);
+    }
+    s_n_iter = 0xffffffffu;
+    s_bad[0] = s_bad[1] = s_bad[2] = 0;
+    fence_mbar_init ();
+  }
+  __syncthreads ();
+
+  auto stage_keys = [&] (int s) { return reinterpret_cast<uint64_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES); };
+  auto stage_cnts = [&] (int s) { return reinterpret_cast<uint32_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES + (size_t) SLOTS * 8); };
+  uint64_t *const sparse_k = reinterpret_cast<uint64_t *> (smem_raw + (size_t) S * Cfg::STAGE_BYTES);
+  uint32_t *const sparse_c = reinterpret_cast<uint32_t *> (smem_raw + (size_t) S * Cfg::STAGE_BYTES + (size_t) KWAY_TILE_CAP * 8);
+  uint16_t *const tab = reinterpret_cast<uint16_t *> (smem_raw + (size_t) S * Cfg::STAGE_BYTES + Cfg::SPARSE_BYTES);
+
+  // ============================================================================ producer (all 32 lanes)
+  if (warp == Cfg::PRODUCER_WARP) {
+    const uint64_t n_tiles = args.n_tiles;
+    uint64_t tile = 0;
+    if (lane == 0) tile = atomicAdd (&args.hdr->ticket, 1u);
+    tile = __shfl_sync (0xffffffffu, tile, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    while (true) {
+      // this tile's slice of every list (lane j < NL) and its key range (lane 0); loaded before the wait
+      uint64_t c_lo = 0, c_hi = 0, k_lo = 0, k_hi = 0;
+      if (tile < n_tiles) {
+        if (lane < NL) {
+          c_lo = args.cuts[tile * NL + lane];
+          c_hi = args.cuts[(tile + 1) * NL + lane];
+        }
+        if (lane == 0) {
+          k_lo = args.bounds[tile];
+          k_hi = args.bounds[tile + 1];
+        }
+      }
+      mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
+      if (tile >= n_tiles) {
+        // END marker through every stage under the normal protocol (see setop2_stream_kernel)
+        if (lane == 0) {
+          for (int q = 0; q < (COUNT_ONLY ? 1 : S); q++) {
+            if (q > 0) mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
+            s_meta[s].tile = KW_TILE_END;
+            mbar_arrive (&bar_full[s]);
+            if (++s == S) { s = 0; ph ^= 1u; }
+          }
+        }
+        break;
+      }
+      const uint64_t n_list = (lane < NL) ? args.n[lane] : 0;
+      const bool sane = c_hi >= c_lo && c_hi <= n_list && c_hi - c_lo <= (uint64_t) KWAY_TILE_CAP;
+      int n = sane ? (int) (c_hi - c_lo) : 0;
+      int total = n;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync (0xffffffffu, total, off);
+      const bool any_bad = __any_sync (0xffffffffu, !sane);
+      if (any_bad || total > KWAY_TILE_CAP) {
+        if (lane == 0) args.hdr->overflow = any_bad ? 2u : 3u;     // unsorted input / a tile the sampling bound does not cover
+        n = 0;
+        total = 0;
+      }
+      const int pc = (int) (c_lo & 3u);                             // count phase inside its 16-byte group
+      const int width = n ? ((pc + n + 3) & ~3) : 0;
+      int incl = width;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync (0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      const int slot0 = incl - width + pc;                          // slot of the slice's first record
+      KwMeta<NL> &m = s_meta[s];
+      if (lane < NL) {
+        m.idx0[lane] = (uint16_t) slot0;
+        m.n[lane] = (uint16_t) n;
+      }
+      if (lane == 0) {
+        m.tile = tile;
+        m.n_total = total;
+        const uint64_t span1 = k_hi >= k_lo ? k_hi - k_lo : 0;      // span - 1
+        const int bits = span1 ? 64 - __clzll ((long long) span1) : 0;
+        const int sh = bits > 32 ? bits - 32 : 0;
+        m.lo = k_lo;
+        m.hi = k_hi;
+        m.sh = sh;
+        m.mult = ((uint64_t) NB << 32) / ((span1 >> sh) + 1ull);
+      }
+      // one block per lane: lanes 2j / 2j + 1 stage the keys / counts of list j
+      const int j = lane >> 1, kind = lane & 1;
+      const uint64_t b_lo = __shfl_sync (0xffffffffu, c_lo, j);
+      const int b_n = __shfl_sync (0xffffffffu, n, j);
+      const int b_slot = __shfl_sync (0xffffffffu, slot0, j);
+      uint32_t tma_bytes = 0;
+      const unsigned char *tma_src = nullptr;
+      unsigned char *tma_dst = nullptr;
+      if (lane < 2 * NL && b_n > 0) {
+        const int es = kind ? 4 : 8;
+        const uint64_t al = kind ? 4 : 2;                           // records per 16 bytes
+        const unsigned char *arr = kind ? reinterpret_cast<const unsigned char *> (args.counts[j]) : reinterpret_cast<const unsigned char *> (args.words[j]);
+        unsigned char *blk = kind ? reinterpret_cast<unsigned char *> (stage_cnts (s)) : reinterpret_cast<unsigned char *> (stage_keys (s));
+        const uint64_t first = b_lo & ~(al - 1);
+        const uint64_t last = (b_lo + (uint64_t) b_n + al - 1) & ~(al - 1);
+        const uint64_t interior = args.n[j] & ~(al - 1);            // the array's 16-byte aligned interior (its base is aligned)
+        const uint64_t t_last = last < interior ? last : interior;
+        const long long dst0 = (long long) b_slot - (long long) (b_lo - first);
+        if (t_last > first) {
+          tma_bytes = (uint32_t) ((t_last - first) * es);
+          tma_src = arr + first * es;
+          tma_dst = blk + dst0 * es;
+        }
+        // records of the slice beyond the aligned interior (the unaligned tail of the array): plain loads
+        for (uint64_t e = (t_last > b_lo ? t_last : b_lo); e < b_lo + (uint64_t) b_n; e++) {
+          const long long d = dst0 + (long long) (e - first);
+          if (kind) reinterpret_cast<uint32_t *> (blk)[d] = reinterpret_cast<const uint32_t *> (arr)[e];
+          else reinterpret_cast<uint64_t *> (blk)[d] = reinterpret_cast<const uint64_t *> (arr)[e];
+        }
+      }
+      uint32_t tx = tma_bytes;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) tx += __shfl_xor_sync (0xffffffffu, tx, off);
+      __syncwarp ();                   // meta and hand-copied records of all lanes are ordered before lane 0's arrive (release)
+      if (lane == 0) mbar_arrive_expect_tx (&bar_full[s], tx);
+      __syncwarp ();
+      if (tma_bytes) bulk_g2s (tma_dst, tma_src, tma_bytes, &bar_full[s]);
+      if (lane == 0) tile = atomicAdd (&args.hdr->ticket, 1u);
+      tile = __shfl_sync (0xffffffffu, tile, 0);
+      if (++s == S) { s = 0; ph ^= 1u; }
+    }
+    return;
+  }
+
+  // ============================================================================ look-back (one warp per stage)
+  if (warp >= Cfg::LOOKBACK_WARP0 && warp < Cfg::STORE_WARP0) {
+    if (COUNT_ONLY) return;
+    const int s = warp - Cfg::LOOKBACK_WARP0;
+    uint32_t ph = 0;
+    for (uint32_t it = (uint32_t) s;; it += S, ph ^= 1u) {
+      mbar_wait_relaxed (&bar_agg[s], ph);
+      if (it >= s_n_iter) break;
+      const uint64_t tile = s_mail[s].tile;
+      const uint64_t base = lookback_exclusive<KW_LB_W> (args.desc, tile, (uint64_t) s_mail[s].cnt, lane);
+      if (lane == 0) {
+        s_mail[s].base = base;
+        mbar_arrive (&bar_base[s]);
+      }
+      __syncwarp ();
+    }
+    return;
+  }
+
+  // ============================================================================ store warps
+  if (warp >= Cfg::STORE_WARP0) {
+    if (COUNT_ONLY) return;
+    const int st_tid = tid - Cfg::STORE_WARP0 * 32;
+    constexpr int ST_THREADS = 32 * KW_STORE_WARPS;
+    int s = 0;
+    uint32_t ph = 0;
+    while (true) {
+      mbar_wait_relaxed (&bar_comp[s], ph);
+      if (s_mail[s].tile == KW_TILE_END) break;
+      mbar_wait_relaxed (&bar_base[s], ph);
+      const uint64_t base = s_mail[s].base;
+      const int cnt = s_mail[s].cnt;
+      const uint64_t *sk = stage_keys (s);
+      const uint32_t *sc = stage_cnts (s);
+      if (base + (uint64_t) cnt <= args.out_capacity) {
+        uint64_t *ow = args.out_words + base;
+        uint32_t *oc = args.out_counts + base;
+        int x = st_tid;
+        for (; x + 7 * ST_THREADS < cnt; x += 8 * ST_THREADS) {
+          uint64_t k[8];
+#pragma unroll
+          for (int r = 0; r < 8; r++) k[r] = sk[x + r * ST_THREADS];
+#pragma unroll
+          for (int r = 0; r < 8; r++) ow[x + r * ST_THREADS] = k[r];
+        }
+        for (; x < cnt; x += ST_THREADS) ow[x] = sk[x];
+        x = st_tid;
+        for (; x + 7 * ST_THREADS < cnt; x += 8 * ST_THREADS) {
+          uint32_t c[8];
+#pragma unroll
+          for (int r = 0; r < 8; r++) c[r] = sc[x + r * ST_THREADS];
+#pragma unroll
+          for (int r = 0; r < 8; r++) oc[x + r * ST_THREADS] = c[r];
+        }
+        for (; x < cnt; x += ST_THREADS) oc[x] = sc[x];
+      } else if (st_tid == 0) {
+        args.hdr->overflow = 1u;
+      }
+      fence_proxy_async ();
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (&bar_empty[s]);
+      if (++s == S) { s = 0; ph ^= 1u; }
+    }
+    return;
+  }
+
+  // ============================================================================ consumers
+  unsigned long long acc_n = 0, acc_sum = 0;
+  int s = 0, n_end = 0;
+  uint32_t ph = 0;
+  const bool is_isect = args.op != 0;
+  const int n_real = args.n_real;
+  const int rule = args.rule;
+  const uint32_t cutoff = args.final_pass ? args.cutoff : 0u;
+  for (uint32_t it = 0;; it++) {
+    mbar_wait (&bar_full[s], ph);
+    const KwMeta<NL> &m = s_meta[s];
+    if (m.tile == KW_TILE_END) {
+      if (COUNT_ONLY) break;
+      if (tid == 0) {
+        if (it < s_n_iter) s_n_iter = it;
+        s_mail[s].tile = KW_TILE_END;
+        mbar_arrive (&bar_agg[s]);
+      }
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (&bar_comp[s]);
+      if (++n_end == S) break;
+      if (++s == S) { s = 0; ph ^= 1u; }
+      continue;
+    }
+    uint64_t *sk = stage_keys (s);
+    uint32_t *sc = stage_cnts (s);
+    const uint64_t lo = m.lo, hi = m.hi, mult = m.mult;
+    const int sh = m.sh;
+    const uint64_t tile_id = m.tile;
+
+    // ---- (1) where does every bucket start in every slice?
+    int base[NL];
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+      const int nj = m.n[j];
+      base[j] = m.idx0[j];
+      uint16_t *tj = tab + j * TS;
+      if (nj == 0) {
+        for (int b = tid; b <= NB; b += NC) tj[b] = (uint16_t) base[j];
+        continue;
+      }
+      for (int i = tid; i < nj; i += NC) {
+        const uint64_t k = sk[base[j] + i];
+        const unsigned b = kw_bucket (k, lo, sh, mult, NB);
+        unsigned from = 0;
+        bool bad = false;
+        if (i > 0) {
+          const uint64_t kp = sk[base[j] + i - 1];
+          from = kw_bucket (kp, lo, sh, mult, NB) + 1u;
+          bad = !(kp < k);
+        } else {
+          bad = k < lo;
+        }
+        if (i == nj - 1) {
+          bad |= k > hi;
+          for (unsigned bb = b + 1; bb <= (unsigned) NB; bb++) tj[bb] = (uint16_t) (base[j] + nj);
+        }
+        if (bad) s_bad[it % 3u] = 1;
+        for (unsigned bb = from; bb <= b; bb++) tj[bb] = (uint16_t) (base[j] + i);
+      }
+    }
+    consumer_sync<NC> ();
+    if (tid == 0) s_bad[(it + 2u) % 3u] = 0;
+    const bool tile_bad = s_bad[it % 3u] != 0;
+    if (tile_bad && tid == 0) args.hdr->overflow = 2u;
+
+    // ---- (2) this thread's bucket: N slice heads in registers
+    int idx[NL], end[NL];
+    uint64_t head[NL];
+    int remaining = 0, sparse_off = 0;
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+      idx[j] = tab[j * TS + tid];
+      end[j] = tile_bad ? idx[j] : (int) tab[j * TS + tid + 1];
+      sparse_off += idx[j] - base[j];
+      remaining += end[j] - idx[j];
+      head[j] = (idx[j] < end[j]) ? sk[idx[j]] : ~0ull;
+    }
+    int pos = sparse_off;
+    while (remaining > 0) {
+      uint64_t mn = head[0];
+#pragma unroll
+      for (int j = 1; j < NL; j++) mn = head[j] < mn ? head[j] : mn;
+      uint32_t f = 0;
+      int n_hit = 0;
+#pragma unroll
+      for (int j = 0; j < NL; j++) {
+        if (idx[j] < end[j] && head[j] == mn) {
+          f = kw_fold<MODE> (f, sc[idx[j]], n_hit == 0, rule);
+          n_hit += 1;
+          idx[j] += 1;
+          head[j] = (idx[j] < end[j]) ? sk[idx[j]] : ~0ull;
+        }
+      }
+      remaining -= n_hit;
+      if (MODE == KWAY_MODE_GENERIC && rule == RULE_NUMBER) f = args.count_override;
+      bool keep = f >= cutoff;
+      if (MODE == KWAY_MODE_I_MIN || (MODE == KWAY_MODE_GENERIC && is_isect)) keep = keep && n_hit == n_real;
+      if (keep) {
+        if (!COUNT_ONLY) {
+          sparse_k[pos] = mn;
+          sparse_c[pos] = f;
+        }
+        pos += 1;
+        acc_sum += f;
+      }
+    }
+    const int cnt = pos - sparse_off;
+    acc_n += (unsigned) cnt;
+
+    if (COUNT_ONLY) {
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (&bar_empty[s]);
+      if (++s == S) { s = 0; ph ^= 1u; }
+      continue;
+    }
+
+    // ---- (3) block scan of the survivor counts, tile total to the look-back warp, compaction
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync (0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_wcnt[it & 1][warp] = incl;
+    consumer_sync<NC> ();             // also: every consumer is done reading this stage's slices
+    static_assert (NWARPS <= 32, "one lane per consumer warp");
+    const int wv = (lane < NWARPS) ? s_wcnt[it & 1][lane] : 0;
+    int wincl = wv;
+#pragma unroll
+    for (int off = 1; off < NWARPS; off <<= 1) {
+      const int t = __shfl_up_sync (0xffffffffu, wincl, off);
+      if (lane >= off) wincl += t;
+    }
+    const int tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
+    const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
+    if (tid == 0) {
+      s_mail[s].tile = tile_id;
+      s_mail[s].cnt = tile_cnt;
+      mbar_arrive (&bar_agg[s]);
+    }
+    const int dst = warp_prefix + incl - cnt;
+    for (int q = 0; q < cnt; q++) {
+      sk[dst + q] = sparse_k[sparse_off + q];
+      sc[dst + q] = sparse_c[sparse_off + q];
+    }
+    __syncwarp ();
+    if (lane == 0) mbar_arrive (&bar_comp[s]);
+    if (++s == S) { s = 0; ph ^= 1u; }
+  }
+
+  acc_n = warp_sum_u64 (acc_n);
+  acc_sum = warp_sum_u64 (acc_sum);
+  if (lane == 0) {
+    s_red[0][warp] = acc_n;
+    s_red[1][warp] = acc_sum;
+  }
+  consumer_sync<NC> ();
+  if (tid == 0) {
+    unsigned long long n = 0, sum = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; w++) {
+      n += s_red[0][w];
+      sum += s_red[1][w];
+    }
+    unsigned long long *slot = args.hdr->totals[0][blockIdx.x & (TOTAL_SLOTS - 1)];
+    atomicAdd (slot, n);
+    atomicAdd (slot + 1, sum);
+  }
+}
+
+// ---- pre-passes --------------------------------------------------------------------------------
+
+// samples[sample_off[j] + i] = words_j[(i + 1) * KWAY_SAMPLE - 1]
+__global__ void __launch_bounds__ (256)
+kway_sample_kernel (const KwayArgs args, uint64_t n_samples, uint64_t *__restrict__ samples)
+{
+  const uint64_t g = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_samples) return;
+  int j = 0;
+#pragma unroll
+  for (int q = 1; q < KWAY_MAX_LISTS; q++)
+    if (q < args.n_lists && g >= args.sample_off[q]) j = q;
+  const uint64_t i = g - args.sample_off[j];
+  samples[g] = args.words[j][(i + 1) * KWAY_SAMPLE - 1];
+}
+
+// cuts[t * NL + j] = number of words of list j below the t-th boundary key (sorted[t * m]); bounds[t] = that key.
+// Thread order: neighbouring threads search neighbouring boundaries in the same list (shared search paths).
+__global__ void __launch_bounds__ (256)
+kway_cuts_kernel (const KwayArgs args, const uint64_t *__restrict__ sorted, uint64_t m, int nl, uint64_t *__restrict__ cuts, uint64_t *__restrict__ bounds)
+{
+  const uint64_t g = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t per_list = args.n_tiles + 1;
+  if (g >= per_list * (uint64_t) nl) return;
+  const int j = (int) (g / per_list);
+  const uint64_t t = g - (uint64_t) j * per_list;
+  const uint64_t n = args.n[j];
+  uint64_t cut;
+  if (t == 0) cut = 0;
+  else if (t == args.n_tiles) cut = n;
+  else {
+    const uint64_t x = sorted[t * m];
+    const uint64_t *w = args.words[j];
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const uint64_t mid = lo + ((hi - lo) >> 1);
+      if (w[mid] < x) lo = mid + 1;
+      else hi = mid;
+    }
+    cut = lo;
+    if (j == 0) bounds[t] = x;
+  }
+  cuts[t * (uint64_t) nl + j] = cut;
+  if (j == 0 && (t == 0 || t == args.n_tiles)) {
+    // the outer bounds: smallest first word / largest last word over the non-empty lists
+    uint64_t v = t == 0 ? ~0ull : 0ull;
+    for (int q = 0; q < args.n_lists; q++) {
+      if (!args.n[q]) continue;
+      const uint64_t e = t == 0 ? args.words[q][0] : args.words[q][args.n[q] - 1];
+      v = t == 0 ? (e < v ? e : v) : (e > v ? e : v);
+    }
+    bounds[t] = v;
+  }
+}
+
+template <int NL, int NC, int S, int MODE, bool CO>
+cudaError_t launch_kway_one (const KwayArgs &args, int sm_count, cudaStream_t st)
+{
+  using Cfg = KwayCfg<NL, NC, S>;
+  auto kernel = kway_tile_kernel<NL, NC, S, MODE, CO>;
+  static bool configured = false;      // benign race: idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  uint64_t grid = (uint64_t) sm_count;
+  if (grid > args.n_tiles) grid = args.n_tiles;
+  kernel<<<(unsigned) grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>> (args);
+  return cudaGetLastError ();
+}
+
+template <int NL, int NC, int S>
+cudaError_t launch_kway_mode (const KwayArgs &args, int mode, bool count_only, int sm_count, cudaStream_t st)
+{
+#define GT4_KW(MODE)                                                                                      \
+  return count_only ? launch_kway_one<NL, NC, S, MODE, true> (args, sm_count, st) : launch_kway_one<NL, NC, S, MODE, false> (args, sm_count, st)
+  switch (mode) {
+  case KWAY_MODE_U_ADD: GT4_KW (KWAY_MODE_U_ADD);
+  case KWAY_MODE_I_MIN: GT4_KW (KWAY_MODE_I_MIN);
+  default:              GT4_KW (KWAY_MODE_GENERIC);
+  }
+#undef GT4_KW
+}
+
+}  // namespace
+
+int kway_select_mode (int op, int rule)
+{
+  if (op == 0 && rule == RULE_ADD) return KWAY_MODE_U_ADD;
+  if (op != 0 && rule == RULE_MIN) return KWAY_MODE_I_MIN;
+  return KWAY_MODE_GENERIC;
+}
+
+cudaError_t launch_kway_samples (const KwayArgs &args, uint64_t n_samples, uint64_t *samples, cudaStream_t st)
+{
+  if (n_samples == 0) return cudaSuccess;
+  kway_sample_kernel<<<(unsigned) ((n_samples + 255) / 256), 256, 0, st>>> (args, n_samples, samples);
+  return cudaGetLastError ();
+}
+
+cudaError_t launch_kway_cuts (const KwayArgs &args, const uint64_t *sorted_samples, uint64_t every, int nl, uint64_t *cuts, uint64_t *bounds, cudaStream_t st)
+{
+  const uint64_t n = (args.n_tiles + 1) * (uint64_t) nl;
+  kway_cuts_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>> (args, sorted_samples, every, nl, cuts, bounds);
+  return cudaGetLastError ();
+}
+
+cudaError_t launch_kway_tiles (const KwayArgs &args, int nl, bool count_only, int sm_count, cudaStream_t st)
+{
+  if (args.n_tiles == 0) return cudaSuccess;
+  const int mode = kway_select_mode (args.op, args.rule);
+  if (nl <= 4) return launch_kway_mode<4, KWAY_CONSUMERS, 3> (args, mode, count_only, sm_count, st);
+  if (nl <= 8) return launch_kway_mode<8, KWAY_CONSUMERS, 3> (args, mode, count_only, sm_count, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace gt4gpu

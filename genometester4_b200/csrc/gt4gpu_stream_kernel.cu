@@ -86,65 +86,6 @@ struct Mailbox {
   int cnt;           // the tile's output count (written by consumer thread 0)
 };
 
-// ---- PTX wrappers ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32 (const void *p) { return (uint32_t) __cvta_generic_to_shared (p); }
-
-__device__ __forceinline__ void mbar_init (uint64_t *bar, uint32_t count)
-{
-  asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive (uint64_t *bar)
-{
-  asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx (uint64_t *bar, uint32_t bytes)
-{
-  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory");
-}
-
-// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out, so a
-// waiting warp does not burn issue slots polling
-__device__ __forceinline__ bool mbar_try_wait (uint64_t *bar, uint32_t parity, uint32_t hint_ns)
-{
-  uint32_t ok;
-  asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok) : "r"(smem_u32 (bar)), "r"(parity), "r"(hint_ns) : "memory");
-  return ok != 0;
-}
-
-__device__ __forceinline__ void mbar_wait (uint64_t *bar, uint32_t parity)
-{
-  while (!mbar_try_wait (bar, parity, 2000u)) { }
-}
-
-// helper warps (producer, look-back, store) can afford to sleep longer
-__device__ __forceinline__ void mbar_wait_relaxed (uint64_t *bar, uint32_t parity)
-{
-  while (!mbar_try_wait (bar, parity, 20000u)) { }
-}
-
-// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s (void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                :: "r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
-}
-
-// L2 prefetch of a byte range (widened inwards to 16-byte boundaries; a few edge bytes do not matter)
-__device__ __forceinline__ void prefetch_l2 (const void *p, uint64_t bytes)
-{
-  const uintptr_t lo = ((uintptr_t) p + 15) & ~(uintptr_t) 15;
-  const uintptr_t hi = ((uintptr_t) p + bytes) & ~(uintptr_t) 15;
-  if (hi > lo) asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(lo), "r"((uint32_t) (hi - lo)) : "memory");
-}
-
-__device__ __forceinline__ void fence_proxy_async () { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init () { asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-template <int NC>
-__device__ __forceinline__ void consumer_sync () { asm volatile ("bar.sync 1, %0;" :: "n"(NC) : "memory"); }
-
 // All 32 lanes of the look-back warp; returns the exclusive prefix of `aggregate`.
 //
 // The chain of prefixes has to advance as fast as tiles are produced (~50-100 tiles/us at the HBM
