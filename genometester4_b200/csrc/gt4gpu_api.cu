@@ -162,9 +162,11 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
     if (!out[s].caller) {
       out[s].capacity = worst_case (p, s, a.n, b.n);
       int rc = dev_alloc ((void **) &out[s].words, out[s].capacity * sizeof (uint64_t));
-      if (rc) return rc;
-      rc = dev_alloc ((void **) &out[s].counts, out[s].capacity * sizeof (uint32_t));
-      if (rc) return rc;
+      if (!rc) rc = dev_alloc ((void **) &out[s].counts, out[s].capacity * sizeof (uint32_t));
+      if (rc) {           // hand back what this call allocated so far; the caller's buffers stay untouched
+        for (int q = 0; q <= s; q++) if (((stream_mask >> q) & 1u) && !out[q].caller) { dev_free (out[q].words); dev_free (out[q].counts); out[q].words = nullptr; out[q].counts = nullptr; }
+        return rc;
+      }
     }
   }
   if (total == 0) return 0;
@@ -236,22 +238,14 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   tl_ms_merge += ms;
   tl_launches += n_launches;
 
-  if (args.debug & 2) {
-    unsigned long long v[4] = {0, 0, 0, 0};
-    for (int k = 0; k < TOTAL_SLOTS; k++) {
-      v[0] += h.totals[(args.stream0 + 1) & 3][k][0]; v[1] += h.totals[(args.stream0 + 1) & 3][k][1];
-      v[2] += h.totals[(args.stream0 + 2) & 3][k][0]; v[3] += h.totals[(args.stream0 + 2) & 3][k][1];
-    }
-    if (v[3]) fprintf (stderr, "gt4gpu debug: look-backs %llu, mean %.0f cycles, %.2f polls, %.2f extra hops\n", v[3],
-                       (double) v[0] / v[3], (double) v[1] / v[3], (double) v[2] / v[3] - 1.0);
-  }
-  if (args.debug & 32) {
-    unsigned long long v[6] = {0, 0, 0, 0, 0, 0};
-    for (int k = 0; k < TOTAL_SLOTS; k++)
-      for (int r = 0; r < 3; r++) { v[2 * r] += h.totals[(args.stream0 + 1 + r) & 3][k][0]; v[2 * r + 1] += h.totals[(args.stream0 + 1 + r) & 3][k][1]; }
-    if (v[5]) fprintf (stderr, "gt4gpu debug: consumer warp cycles per tile: wait %.0f search %.0f merge %.0f scan+barrier %.0f scatter %.0f (warp-tiles %llu)\n",
-                       (double) v[0] / v[5], (double) v[1] / v[5], (double) v[2] / v[5], (double) v[3] / v[5], (double) v[4] / v[5], v[5]);
-  }
+  // statistics of the LAST pass only make sense with one switch at a time (bits 2 and 32 share dbg[0..1])
+  if ((args.debug & 2) && !(args.debug & 32) && h.dbg[3])
+    fprintf (stderr, "gt4gpu debug: look-backs %llu, mean %.0f cycles, %.2f polls, %.2f extra hops\n", h.dbg[3],
+             (double) h.dbg[0] / h.dbg[3], (double) h.dbg[1] / h.dbg[3], (double) h.dbg[2] / h.dbg[3] - 1.0);
+  if ((args.debug & 32) && h.dbg[7])
+    fprintf (stderr, "gt4gpu debug: consumer warp cycles per tile: wait %.0f search %.0f merge %.0f scan+barrier %.0f scatter %.0f (warp-tiles %llu)\n",
+             (double) h.dbg[0] / h.dbg[7], (double) h.dbg[1] / h.dbg[7], (double) h.dbg[4] / h.dbg[7], (double) h.dbg[5] / h.dbg[7],
+             (double) h.dbg[6] / h.dbg[7], h.dbg[7]);
   if (h.overflow == 2u) return fail (GT4GPU_ERR_ARG, "input lists are not strictly ascending (the merge result is undefined)");
   if (h.overflow) return fail (GT4GPU_ERR_CAPACITY, "output buffer too small for the merge result");
   for (int s = 0; s < 4; s++) {
@@ -297,11 +291,15 @@ int parse_header (const unsigned char *file, uint64_t size, int mode, const char
     memcpy (&h, file, take);
     if (h.version_minor == 0) h.list_start = 40;
     if (h.version_minor <= 2) { h.word_bytes = 8; h.count_bytes = 4; }
-    const uint64_t need = h.list_start + h.n_words * (uint64_t) (h.word_bytes + h.count_bytes);
-    if (size < need) return fail (GT4GPU_ERR_FORMAT, "%s: file size too small (%llu, should be at least %llu)", path,
-                                  (unsigned long long) size, (unsigned long long) need);
+    // (division form: n_words comes from the file and must not be able to wrap the products)
+    const uint64_t rec_bytes = (uint64_t) h.word_bytes + h.count_bytes;
+    if (h.list_start > size || (rec_bytes && (size - h.list_start) / rec_bytes < h.n_words)) {
+      const uint64_t need = h.list_start + h.n_words * rec_bytes;
+      return fail (GT4GPU_ERR_FORMAT, "%s: file size too small (%llu, should be at least %llu)", path,
+                   (unsigned long long) size, (unsigned long long) need);
+    }
     // the accessors always stride 12 bytes (src/word-map.h:89-99); make sure that stays in bounds
-    if (size < h.list_start + h.n_words * 12ull) return fail (GT4GPU_ERR_FORMAT, "%s: records exceed the file", path);
+    if ((size - h.list_start) / 12ull < h.n_words) return fail (GT4GPU_ERR_FORMAT, "%s: records exceed the file", path);
   } else {
     if (size < 48) return fail (GT4GPU_ERR_FORMAT, "%s: could not read list header", path);
     memcpy (&h, file, 48);
@@ -309,7 +307,7 @@ int parse_header (const unsigned char *file, uint64_t size, int mode, const char
     if (h.version_major > GT4GPU_VERSION_MAJOR)
       return fail (GT4GPU_ERR_FORMAT, "%s: incompatible major version %u (required %u)", path, h.version_major, GT4GPU_VERSION_MAJOR);
     if (h.version_major == 4 && h.version_minor == 0) h.list_start = 48;
-    if (size < h.list_start + h.n_words * 12ull) return fail (GT4GPU_ERR_FORMAT, "%s: records exceed the file", path);
+    if (h.list_start > size || (size - h.list_start) / 12ull < h.n_words) return fail (GT4GPU_ERR_FORMAT, "%s: records exceed the file", path);
   }
   *out = h;
   return 0;
@@ -685,7 +683,10 @@ int kway_pass (const std::vector<DevList> &lists, int op, int rule, uint32_t cut
     smallest = std::min (smallest, l.n);
   }
   const int nl = n_lists <= 4 ? 4 : 8;
-  const uint64_t every = (uint64_t) (KWAY_TILE_CAP / KWAY_SAMPLE - n_lists - 2);       // samples per tile
+  // samples per tile: a tile holds every * KWAY_SAMPLE records on average and at most (every + 2 n_lists) * KWAY_SAMPLE; lists
+  // whose words interleave evenly stay within +- n_lists / 2 samples of the average, anything beyond the capacity is
+  // caught by the kernel (overflow 3) and the call falls back to the tree of two-list merges
+  const uint64_t every = (uint64_t) (KWAY_TILE_CAP / KWAY_SAMPLE - std::max (2, n_lists / 2) - 2);
   const uint64_t n_tiles = n_samples ? (n_samples - 1) / every + 1 : 1;
   cudaStream_t st = g_ctx.stream;
 
@@ -771,6 +772,10 @@ int kway_pass (const std::vector<DevList> &lists, int op, int rule, uint32_t cut
   cudaEventElapsedTime (&ms, tl_ev[1], tl_ev[2]);
   tl_ms_merge += ms;
   tl_launches += n_launches;
+  if ((args.debug & 32) && h.dbg[7])
+    fprintf (stderr, "gt4gpu debug: k-way consumer warp cycles per tile: wait %.0f tables %.0f merge %.0f scan+barrier %.0f compaction %.0f (warp-tiles %llu, tiles %llu)\n",
+             (double) h.dbg[0] / h.dbg[7], (double) h.dbg[1] / h.dbg[7], (double) h.dbg[4] / h.dbg[7], (double) h.dbg[5] / h.dbg[7],
+             (double) h.dbg[6] / h.dbg[7], h.dbg[7], (unsigned long long) n_tiles);
   if (h.overflow) {
     if (own_out) free_out (*out);
     if (h.overflow == 3u) { *fallback = true; return 0; }
@@ -1316,11 +1321,10 @@ int gt4gpu_union_matrix (const gt4gpu_list *const *lists, unsigned n_lists, int 
   // those rows: one after each word that ends some list, unless it is the overall last word.
   std::vector<uint64_t> last_words;
   if (!is_union) {
-    std::vector<uint64_t> tmp (1);
-    for (unsigned j = 0; j < n_lists; j++) {
-      cudaMemcpy (tmp.data (), lists[j]->words + lists[j]->n_words - 1, sizeof (uint64_t), cudaMemcpyDeviceToHost);
-      last_words.push_back (tmp[0]);
-    }
+    last_words.resize (n_lists);
+    for (unsigned j = 0; j < n_lists; j++)
+      CU (cudaMemcpyAsync (&last_words[j], lists[j]->words + lists[j]->n_words - 1, sizeof (uint64_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+    CU (cudaStreamSynchronize (g_ctx.stream));
     std::sort (last_words.begin (), last_words.end ());
     last_words.erase (std::unique (last_words.begin (), last_words.end ()), last_words.end ());
   }
@@ -1628,9 +1632,13 @@ int gt4gpu_count_words (const uint64_t *words, uint64_t n_words, int on_device, 
   first = (uint64_t *) tmp.p[3]; ws_rle = (unsigned char *) tmp.p[4];
   unsigned long long *d_unique = nullptr;
   CU (launch_rle_heads (sorted, n, words_tmp, first, ws_rle, g_ctx.sm_count, &d_unique, st));
-  unsigned long long n_unique = 0;
+  unsigned long long n_unique = 0, or_all = 0;
   CU (cudaMemcpyAsync (&n_unique, d_unique, sizeof (n_unique), cudaMemcpyDeviceToHost, st));
+  CU (cudaMemcpyAsync (&or_all, ws_sort + SORT_OR_OFFSET, sizeof (or_all), cudaMemcpyDeviceToHost, st));
   CU (cudaStreamSynchronize (st));
+  // only the low 2k bits were sorted: a word >= 4^k would have left the table unsorted (and the list malformed)
+  if (word_length < 32 && (or_all >> (2 * word_length)) != 0)
+    return fail (GT4GPU_ERR_ARG, "gt4gpu_count_words: a word does not fit %u nucleotides (OR of all words = %llx)", word_length, or_all);
   if (n_unique == 0 || n_unique > n) return fail (GT4GPU_ERR_CUDA, "run-length pass returned %llu runs for %llu words", n_unique, (unsigned long long) n);
 
   uint64_t *res_words = nullptr;

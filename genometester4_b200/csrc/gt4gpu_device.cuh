@@ -124,6 +124,12 @@ __device__ __forceinline__ void mbar_wait_relaxed (uint64_t *bar, uint32_t parit
   while (!mbar_try_wait (bar, parity, 20000u)) { }
 }
 
+// same, giving the issue slots to the other warps between two looks (try_wait comes back long before its time hint)
+__device__ __forceinline__ void mbar_wait_sleep (uint64_t *bar, uint32_t parity, unsigned ns)
+{
+  while (!mbar_try_wait (bar, parity, 20000u)) __nanosleep (ns);
+}
+
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {

@@ -28,6 +28,7 @@ struct CallHeader {
   uint32_t ticket;
   uint32_t overflow;
   unsigned long long totals[4][TOTAL_SLOTS][2];
+  unsigned long long dbg[8];      // GT4GPU_DEBUG statistics (look-back latency, consumer phase cycles); never read by the merge logic
 };
 
 struct TileArgs {
@@ -123,6 +124,8 @@ cudaError_t launch_lookup_sorted (const uint64_t *words, const uint32_t *counts,
 // ---- list building (gt4gpu_sort_kernel.cu): least-significant-digit radix sort of raw words + run-length counts
 static constexpr int SORT_MAX_PASSES = 8;                                        // 8-bit digits of a 64-bit word
 static constexpr size_t SORT_SCRATCH_HEAD = 2 * SORT_MAX_PASSES * 256 * 8 + 256;  // histograms, bin starts, tickets
+static constexpr int SORT_OR_SLOT = 8;           // u64 slot after the tickets: OR of all keys (written by the histogram pass)
+static constexpr size_t SORT_OR_OFFSET = 2 * SORT_MAX_PASSES * 256 * 8 + SORT_OR_SLOT * 8;   // its byte offset in the scratch
 size_t sort_scratch_bytes (uint64_t n);
 cudaError_t launch_radix_sort (const uint64_t *input, uint64_t *keys, uint64_t *alt, uint64_t n, int n_pass, unsigned char *scratch,
                                int sm_count, uint64_t **sorted, cudaStream_t st);

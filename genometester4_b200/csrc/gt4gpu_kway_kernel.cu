@@ -30,6 +30,7 @@
 // HBM-bound integer work: no tensor cores.  Algorithmic traffic 12 B per input record + 12 B per output record.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gt4gpu_device.cuh"
 #include "gt4gpu_internal.h"
@@ -56,9 +57,11 @@ struct KwayCfg {
   static constexpr int SLOTS = KWAY_TILE_CAP + 8 * NL + 8;
   static constexpr size_t STAGE_BYTES = (size_t) SLOTS * 12;
   static constexpr size_t SPARSE_BYTES = (size_t) KWAY_TILE_CAP * 12;
-  static constexpr int TAB_STRIDE = NB + 2;
-  static constexpr size_t TAB_BYTES = ((size_t) NL * TAB_STRIDE * 2 + 15) & ~(size_t) 15;
-  static constexpr size_t SMEM_BYTES = S * STAGE_BYTES + SPARSE_BYTES + TAB_BYTES;
+  static constexpr size_t HIST_BYTES = (size_t) NL * NB * 4;      // records of every slice in every bucket
+  static constexpr size_t SMEM_BYTES = S * STAGE_BYTES + SPARSE_BYTES + HIST_BYTES;
+  static constexpr int LOG2_NB = NB == 128 ? 7 : NB == 256 ? 8 : 9;
+  static constexpr int BUCKET_SHIFT = 30 - LOG2_NB;               // bucket = umulhi (u, mult) >> BUCKET_SHIFT, mult < 2^32
+  static_assert (NB == 128 || NB == 256 || NB == 512, "bucket count");
   static_assert (SLOTS % 4 == 0, "the count region must start 16-byte aligned");
   static_assert (SLOTS < 65536, "slot indices are kept as u16");
 };
@@ -68,8 +71,8 @@ struct KwMeta {
   uint64_t tile;      // KW_TILE_END: no more work
   uint64_t lo;        // smallest key the tile can hold
   uint64_t hi;        // largest key the tile can hold
-  uint64_t mult;      // bucket = (((key - lo) >> sh) * mult) >> 32
-  int sh;
+  uint32_t mult;      // bucket = umulhi (u, mult) >> BUCKET_SHIFT with u = high word of (key - lo) << lsh
+  int lsh;            // leading zeros of hi - lo: the tile's key span is normalised to 32 significant bits
   int n_total;
   uint16_t idx0[NL];  // slot of the slice's first record (keys and counts share the index space)
   uint16_t n[NL];
@@ -81,10 +84,15 @@ struct KwMailbox {
   int cnt;
 };
 
-__device__ __forceinline__ unsigned kw_bucket (uint64_t key, uint64_t lo, int sh, uint64_t mult, unsigned nb)
+// Bucket of a key: the tile's key span [lo, hi] is normalised to 32 significant bits (u) and scaled to NB buckets with
+// one multiply; monotone in the key, < NB for lo <= key <= hi (the clamp only matters for lists that are not sorted).
+template <int SHIFT>
+__device__ __forceinline__ unsigned kw_bucket (uint64_t key, uint64_t lo, int lsh, uint32_t mult, unsigned nb)
 {
-  const uint64_t d = ((key - lo) >> sh) & 0xffffffffull;
-  const unsigned b = (unsigned) ((d * mult) >> 32);
+  const uint64_t d = key - lo;
+  const uint32_t dl = (uint32_t) d, dh = (uint32_t) (d >> 32);
+  const uint32_t u = (lsh >= 32) ? (dl << (lsh & 31)) : __funnelshift_l (dl, dh, lsh);
+  const unsigned b = __umulhi (u, mult) >> SHIFT;
   return b < nb ? b : nb - 1;
 }
 
@@ -110,7 +118,7 @@ kway_tile_kernel (const KwayArgs args)
   constexpr int NWARPS = Cfg::NWARPS;
   constexpr int NB = Cfg::NB;
   constexpr int SLOTS = Cfg::SLOTS;
-  constexpr int TS = Cfg::TAB_STRIDE;
+  constexpr int BSH = Cfg::BUCKET_SHIFT;
 
   extern __shared__ __align__ (128) unsigned char smem_raw[];
   __shared__ __align__ (8) uint64_t bar_full[S];
@@ -121,7 +129,7 @@ kway_tile_kernel (const KwayArgs args)
   __shared__ KwMeta<NL> s_meta[S];
   __shared__ KwMailbox s_mail[S];
   __shared__ int s_wcnt[2][NWARPS];
-  __shared__ int s_bad[3];
+  __shared__ uint32_t s_wtot[NWARPS][NL / 2];
   __shared__ volatile unsigned int s_n_iter;
   __shared__ unsigned long long s_red[2][NWARPS];
 
@@ -139,7 +147,6 @@ kway_tile_kernel (const KwayArgs args)
       mbar_init (&bar_empty[s], COUNT_ONLY ? NWARPS : KW_STORE_WARPS);
     }
     s_n_iter = 0xffffffffu;
-    s_bad[0] = s_bad[1] = s_bad[2] = 0;
     fence_mbar_init ();
   }
   __syncthreads ();
@@ -148,7 +155,9 @@ kway_tile_kernel (const KwayArgs args)
   auto stage_cnts = [&] (int s) { return reinterpret_cast<uint32_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES + (size_t) SLOTS * 8); };
   uint64_t *const sparse_k = reinterpret_cast<uint64_t *> (smem_raw + (size_t) S * Cfg::STAGE_BYTES);
   uint32_t *const sparse_c = reinterpret_cast<uint32_t *> (smem_raw + (size_t) S * Cfg::STAGE_BYTES + (size_t) KWAY_TILE_CAP * 8);
-  uint16_t *const tab = reinterpret_cast<uint16_t *> (smem_raw + (size_t) S * Cfg::STAGE_BYTES + Cfg::SPARSE_BYTES);
+  uint32_t *const hist = reinterpret_cast<uint32_t *> (smem_raw + (size_t) S * Cfg::STAGE_BYTES + Cfg::SPARSE_BYTES);
+  for (int i = tid; i < NL * NB; i += Cfg::NTHREADS) hist[i] = 0;
+  __syncthreads ();
 
   // ============================================================================ producer (all 32 lanes)
   if (warp == Cfg::PRODUCER_WARP) {
@@ -171,12 +180,12 @@ kway_tile_kernel (const KwayArgs args)
           k_hi = args.bounds[tile + 1];
         }
       }
-      mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
+      mbar_wait_sleep (&bar_empty[s], ph ^ 1u, 200);
       if (tile >= n_tiles) {
         // END marker through every stage under the normal protocol (see setop2_stream_kernel)
         if (lane == 0) {
           for (int q = 0; q < (COUNT_ONLY ? 1 : S); q++) {
-            if (q > 0) mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
+            if (q > 0) mbar_wait_sleep (&bar_empty[s], ph ^ 1u, 200);
             s_meta[s].tile = KW_TILE_END;
             mbar_arrive (&bar_full[s]);
             if (++s == S) { s = 0; ph ^= 1u; }
@@ -214,12 +223,12 @@ kway_tile_kernel (const KwayArgs args)
         m.tile = tile;
         m.n_total = total;
         const uint64_t span1 = k_hi >= k_lo ? k_hi - k_lo : 0;      // span - 1
-        const int bits = span1 ? 64 - __clzll ((long long) span1) : 0;
-        const int sh = bits > 32 ? bits - 32 : 0;
+        const int lsh = span1 ? __clzll ((long long) span1) : 63;
+        const uint64_t top = (span1 << lsh) >> 32;                  // in [2^31, 2^32) unless the span is a single key
         m.lo = k_lo;
         m.hi = k_hi;
-        m.sh = sh;
-        m.mult = ((uint64_t) NB << 32) / ((span1 >> sh) + 1ull);
+        m.lsh = lsh;
+        m.mult = (uint32_t) (((uint64_t) NB << (32 + BSH)) / (top + 1ull));
       }
       // one block per lane: lanes 2j / 2j + 1 stage the keys / counts of list j
       const int j = lane >> 1, kind = lane & 1;
@@ -271,7 +280,7 @@ kway_tile_kernel (const KwayArgs args)
     const int s = warp - Cfg::LOOKBACK_WARP0;
     uint32_t ph = 0;
     for (uint32_t it = (uint32_t) s;; it += S, ph ^= 1u) {
-      mbar_wait_relaxed (&bar_agg[s], ph);
+      mbar_wait_sleep (&bar_agg[s], ph, 200);
       if (it >= s_n_iter) break;
       const uint64_t tile = s_mail[s].tile;
       const uint64_t base = lookback_exclusive<KW_LB_W> (args.desc, tile, (uint64_t) s_mail[s].cnt, lane);
@@ -292,9 +301,9 @@ kway_tile_kernel (const KwayArgs args)
     int s = 0;
     uint32_t ph = 0;
     while (true) {
-      mbar_wait_relaxed (&bar_comp[s], ph);
+      mbar_wait_sleep (&bar_comp[s], ph, 200);
       if (s_mail[s].tile == KW_TILE_END) break;
-      mbar_wait_relaxed (&bar_base[s], ph);
+      mbar_wait_sleep (&bar_base[s], ph, 100);
       const uint64_t base = s_mail[s].base;
       const int cnt = s_mail[s].cnt;
       const uint64_t *sk = stage_keys (s);
@@ -339,8 +348,12 @@ kway_tile_kernel (const KwayArgs args)
   const int n_real = args.n_real;
   const int rule = args.rule;
   const uint32_t cutoff = args.final_pass ? args.cutoff : 0u;
+  const bool prof = (args.debug & 32) != 0;
+  long long t_wait = 0, t_fill = 0, t_loop = 0, t_scan = 0, t_comp = 0, n_prof = 0;
   for (uint32_t it = 0;; it++) {
+    const long long c0 = prof ? clock64 () : 0;
     mbar_wait (&bar_full[s], ph);
+    const long long c1 = prof ? clock64 () : 0;
     const KwMeta<NL> &m = s_meta[s];
     if (m.tile == KW_TILE_END) {
       if (COUNT_ONLY) break;
@@ -357,56 +370,72 @@ kway_tile_kernel (const KwayArgs args)
     }
     uint64_t *sk = stage_keys (s);
     uint32_t *sc = stage_cnts (s);
-    const uint64_t lo = m.lo, hi = m.hi, mult = m.mult;
-    const int sh = m.sh;
+    const uint64_t lo = m.lo;
+    const uint32_t mult = m.mult;
+    const int lsh = m.lsh;
     const uint64_t tile_id = m.tile;
 
-    // ---- (1) where does every bucket start in every slice?
+    // ---- (1) how many records of every slice fall into every bucket?  (hist is all zero between tiles)
     int base[NL];
 #pragma unroll
     for (int j = 0; j < NL; j++) {
       const int nj = m.n[j];
       base[j] = m.idx0[j];
-      uint16_t *tj = tab + j * TS;
-      if (nj == 0) {
-        for (int b = tid; b <= NB; b += NC) tj[b] = (uint16_t) base[j];
-        continue;
-      }
+      uint32_t *hj = hist + j * NB;
       for (int i = tid; i < nj; i += NC) {
         const uint64_t k = sk[base[j] + i];
-        const unsigned b = kw_bucket (k, lo, sh, mult, NB);
-        unsigned from = 0;
-        bool bad = false;
-        if (i > 0) {
-          const uint64_t kp = sk[base[j] + i - 1];
-          from = kw_bucket (kp, lo, sh, mult, NB) + 1u;
-          bad = !(kp < k);
-        } else {
-          bad = k < lo;
-        }
-        if (i == nj - 1) {
-          bad |= k > hi;
-          for (unsigned bb = b + 1; bb <= (unsigned) NB; bb++) tj[bb] = (uint16_t) (base[j] + nj);
-        }
-        if (bad) s_bad[it % 3u] = 1;
-        for (unsigned bb = from; bb <= b; bb++) tj[bb] = (uint16_t) (base[j] + i);
+        if (i > 0 && !(sk[base[j] + i - 1] < k)) args.hdr->overflow = 2u;      // not strictly ascending: reported, result undefined
+        atomicAdd (&hj[kw_bucket<BSH> (k, lo, lsh, mult, NB)], 1u);
       }
     }
     consumer_sync<NC> ();
-    if (tid == 0) s_bad[(it + 2u) % 3u] = 0;
-    const bool tile_bad = s_bad[it % 3u] != 0;
-    if (tile_bad && tid == 0) args.hdr->overflow = 2u;
 
-    // ---- (2) this thread's bucket: N slice heads in registers
+    // ---- (2) this thread's bucket: exclusive prefix of the bucket counts over the threads, two lists per 32-bit word
+    uint32_t hcnt[NL];
+    uint32_t pk[NL / 2];
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+      hcnt[j] = hist[j * NB + tid];
+      hist[j * NB + tid] = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < NL / 2; q++) pk[q] = hcnt[2 * q] | (hcnt[2 * q + 1] << 16);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+      for (int q = 0; q < NL / 2; q++) {
+        const uint32_t t = __shfl_up_sync (0xffffffffu, pk[q], off);
+        if (lane >= off) pk[q] += t;
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int q = 0; q < NL / 2; q++) s_wtot[warp][q] = pk[q];
+    }
+    consumer_sync<NC> ();
+#pragma unroll
+    for (int q = 0; q < NL / 2; q++) {
+      uint32_t w = (lane < NWARPS) ? s_wtot[lane][q] : 0u;
+      const uint32_t own = w;
+#pragma unroll
+      for (int off = 1; off < NWARPS; off <<= 1) {
+        const uint32_t t = __shfl_up_sync (0xffffffffu, w, off);
+        if (lane >= off) w += t;
+      }
+      pk[q] += __shfl_sync (0xffffffffu, w - own, warp);
+    }
+    const long long c2 = prof ? clock64 () : 0;
     int idx[NL], end[NL];
     uint64_t head[NL];
     int remaining = 0, sparse_off = 0;
 #pragma unroll
     for (int j = 0; j < NL; j++) {
-      idx[j] = tab[j * TS + tid];
-      end[j] = tile_bad ? idx[j] : (int) tab[j * TS + tid + 1];
-      sparse_off += idx[j] - base[j];
-      remaining += end[j] - idx[j];
+      const int incl_j = (int) ((pk[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+      const int excl_j = incl_j - (int) hcnt[j];
+      idx[j] = base[j] + excl_j;
+      end[j] = idx[j] + (int) hcnt[j];
+      sparse_off += excl_j;
+      remaining += (int) hcnt[j];
       head[j] = (idx[j] < end[j]) ? sk[idx[j]] : ~0ull;
     }
     int pos = sparse_off;
@@ -440,6 +469,8 @@ kway_tile_kernel (const KwayArgs args)
     }
     const int cnt = pos - sparse_off;
     acc_n += (unsigned) cnt;
+    const long long c3 = prof ? clock64 () : 0;
+    if (prof) { t_wait += c1 - c0; t_fill += c2 - c1; t_loop += c3 - c2; n_prof += 1; }
 
     if (COUNT_ONLY) {
       __syncwarp ();
@@ -472,6 +503,7 @@ kway_tile_kernel (const KwayArgs args)
       s_mail[s].cnt = tile_cnt;
       mbar_arrive (&bar_agg[s]);
     }
+    const long long c4 = prof ? clock64 () : 0;
     const int dst = warp_prefix + incl - cnt;
     for (int q = 0; q < cnt; q++) {
       sk[dst + q] = sparse_k[sparse_off + q];
@@ -479,7 +511,13 @@ kway_tile_kernel (const KwayArgs args)
     }
     __syncwarp ();
     if (lane == 0) mbar_arrive (&bar_comp[s]);
+    if (prof) { const long long c5 = clock64 (); t_scan += c4 - c3; t_comp += c5 - c4; }
     if (++s == S) { s = 0; ph ^= 1u; }
+  }
+  if (prof && lane == 0) {       // experiments: per-phase cycles of the consumer warps
+    atomicAdd (&args.hdr->dbg[0], (unsigned long long) t_wait); atomicAdd (&args.hdr->dbg[1], (unsigned long long) t_fill);
+    atomicAdd (&args.hdr->dbg[4], (unsigned long long) t_loop); atomicAdd (&args.hdr->dbg[5], (unsigned long long) t_scan);
+    atomicAdd (&args.hdr->dbg[6], (unsigned long long) t_comp); atomicAdd (&args.hdr->dbg[7], (unsigned long long) n_prof);
   }
 
   acc_n = warp_sum_u64 (acc_n);
@@ -614,8 +652,18 @@ cudaError_t launch_kway_tiles (const KwayArgs &args, int nl, bool count_only, in
 {
   if (args.n_tiles == 0) return cudaSuccess;
   const int mode = kway_select_mode (args.op, args.rule);
+  static int consumers = 0;      // benign race: idempotent
+  if (consumers == 0) {
+    const char *env = getenv ("GT4GPU_KWAY_CONSUMERS");          // experiments: 128 / 256 / 512 consumer threads (8-list variant)
+    const int v = env ? atoi (env) : KWAY_CONSUMERS;
+    consumers = (v == 128 || v == 512) ? v : KWAY_CONSUMERS;
+  }
   if (nl <= 4) return launch_kway_mode<4, KWAY_CONSUMERS, 3> (args, mode, count_only, sm_count, st);
-  if (nl <= 8) return launch_kway_mode<8, KWAY_CONSUMERS, 3> (args, mode, count_only, sm_count, st);
+  if (nl <= 8) {
+    if (consumers == 128) return launch_kway_mode<8, 128, 3> (args, mode, count_only, sm_count, st);
+    if (consumers == 512) return launch_kway_mode<8, 512, 3> (args, mode, count_only, sm_count, st);
+    return launch_kway_mode<8, KWAY_CONSUMERS, 3> (args, mode, count_only, sm_count, st);
+  }
   return cudaErrorInvalidValue;
 }
 

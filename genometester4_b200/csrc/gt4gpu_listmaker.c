@@ -73,6 +73,9 @@ static double t_read = 0, t_sort = 0, t_collate = 0;
 static uint64_t fasta_block = 1ULL << 30;     /* bytes of FastA text parsed per GPU call (GT4GPU_FASTA_BLOCK overrides) */
 static uint64_t fastq_device_max = 8ULL << 30;   /* larger FastQ files take the host reader */
 static unsigned long long n_read = 0;
+static unsigned fold_tables = 16;                /* tables resident before they are folded into one (GT4GPU_FOLD_TABLES) */
+static uint64_t fold_bytes = 32ULL << 30;          /* ... or this many bytes of table records (GT4GPU_FOLD_BYTES) */
+static uint64_t resident_bytes = 0;
 
 static int
 flush_table (const uint64_t *words, uint64_t n, int on_device, unsigned wordlength)
@@ -80,8 +83,9 @@ flush_table (const uint64_t *words, uint64_t n, int on_device, unsigned wordleng
   double t0 = now ();
   int rc;
   if (!n) return 0;
-  if (n_tables >= 4096) {
-    /* fold what we have into one table first (the reference collates 16 files at a time, :822-830) */
+  if (n_tables >= fold_tables || resident_bytes >= fold_bytes) {
+    /* fold what we have into one table first, so that the device only ever holds a bounded number of tables plus the
+     * distinct words seen so far (the reference collates its temporary files 16 at a time, src/glistmaker.c:822-830) */
     gt4gpu_result merged;
     memset (&merged, 0, sizeof (merged));
     rc = gt4gpu_union_multi ((const gt4gpu_list *const *) table_lists, n_tables, 1, GT4GPU_RULE_ADD, 1, 0, &merged);
@@ -91,6 +95,10 @@ flush_table (const uint64_t *words, uint64_t n, int on_device, unsigned wordleng
     rc = gt4gpu_list_from_device (merged.words, merged.counts, merged.n_words, wordlength, &table_lists[0]);
     if (rc) return rc;
     n_tables = 1;
+    resident_bytes = merged.n_words * 12ULL;
+    /* the folded table itself may exceed the budget: leave room for as many new words again before the next fold */
+    if (resident_bytes >= fold_bytes / 2) fold_bytes = resident_bytes * 2;
+    if (debug) fprintf (stderr, "Folded tables: %llu unique\n", (unsigned long long) merged.n_words);
   }
   memset (&tables[n_tables], 0, sizeof (tables[0]));
   rc = gt4gpu_count_words (words, n, on_device, wordlength, &tables[n_tables]);
@@ -98,6 +106,7 @@ flush_table (const uint64_t *words, uint64_t n, int on_device, unsigned wordleng
   rc = gt4gpu_list_from_device (tables[n_tables].words, tables[n_tables].counts, tables[n_tables].n_words, wordlength, &table_lists[n_tables]);
   if (rc) return rc;
   if (debug) fprintf (stderr, "Table %u: %llu words, %llu unique\n", n_tables, (unsigned long long) n, (unsigned long long) tables[n_tables].n_words);
+  resident_bytes += tables[n_tables].n_words * 12ULL;
   n_tables += 1;
   t_sort += now () - t0;
   return 0;
@@ -201,6 +210,10 @@ main (int argc, const char *argv[])
   }
   if (tablesize < 1) tablesize = 1;
   if (getenv ("GT4GPU_FASTA_BLOCK")) fasta_block = strtoull (getenv ("GT4GPU_FASTA_BLOCK"), NULL, 10);
+  if (getenv ("GT4GPU_FOLD_TABLES")) fold_tables = (unsigned) strtoul (getenv ("GT4GPU_FOLD_TABLES"), NULL, 10);
+  if (getenv ("GT4GPU_FOLD_BYTES")) fold_bytes = strtoull (getenv ("GT4GPU_FOLD_BYTES"), NULL, 10);
+  if (fold_tables < 2) fold_tables = 2;
+  if (fold_tables > 4096) fold_tables = 4096;
   if (fasta_block < 1) fasta_block = 1;
   for (i = 0; i < n_inputs; i++) {
     struct stat s;
@@ -339,6 +352,7 @@ main (int argc, const char *argv[])
     continue;
 gpu_error:
     fprintf (stderr, "Error: %s\n", gt4gpu_last_error ());
+    free (words);
     return 1;
   }
   if (table_fill) {

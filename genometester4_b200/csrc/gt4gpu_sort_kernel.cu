@@ -60,8 +60,9 @@ using namespace dev;
 constexpr int HIST_COPIES = 4;     // privatised per group of warps: fewer same-address shared atomics
 
 __global__ void __launch_bounds__ (512)
-radix_hist_kernel (const uint64_t *__restrict__ keys, uint64_t n, int n_pass, unsigned long long *__restrict__ hist)
+radix_hist_kernel (const uint64_t *__restrict__ keys, uint64_t n, int n_pass, unsigned long long *__restrict__ hist, unsigned long long *__restrict__ or_all)
 {
+  uint64_t seen = 0;       // OR of every key: the caller checks that no bit above the sorted digits is set
   __shared__ uint32_t s_hist[HIST_COPIES][SORT_MAX_PASSES][RADIX];
   for (int i = threadIdx.x; i < HIST_COPIES * SORT_MAX_PASSES * RADIX; i += blockDim.x) (&s_hist[0][0][0])[i] = 0;
   __syncthreads ();
@@ -77,13 +78,19 @@ radix_hist_kernel (const uint64_t *__restrict__ keys, uint64_t n, int n_pass, un
 #pragma unroll
     for (int u = 0; u < U; u++) key[u] = keys[i + u * (uint64_t) blockDim.x];
 #pragma unroll
-    for (int u = 0; u < U; u++)
+    for (int u = 0; u < U; u++) {
+      seen |= key[u];
       for (int p = 0; p < n_pass; p++) atomicAdd (&mine[p][(key[u] >> (8 * p)) & 255u], 1u);
+    }
   }
   for (; i < hi; i += blockDim.x) {
     const uint64_t key = keys[i];
+    seen |= key;
     for (int p = 0; p < n_pass; p++) atomicAdd (&mine[p][(key >> (8 * p)) & 255u], 1u);
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) seen |= __shfl_xor_sync (0xffffffffu, seen, off);
+  if ((threadIdx.x & 31) == 0 && seen) atomicOr (or_all, (unsigned long long) seen);
   __syncthreads ();
   for (int i = threadIdx.x; i < n_pass * RADIX; i += blockDim.x) {
     unsigned long long sum = 0;
@@ -458,7 +465,7 @@ static cudaError_t radix_sort_impl (const uint64_t *input, uint64_t *keys, uint6
 
   uint64_t hist_grid = (uint64_t) sm_count * 2;
   if (hist_grid > (n + 511) / 512) hist_grid = (n + 511) / 512;
-  radix_hist_kernel<<<(unsigned) hist_grid, 512, 0, st>>> (input, n, n_pass, hist);
+  radix_hist_kernel<<<(unsigned) hist_grid, 512, 0, st>>> (input, n, n_pass, hist, reinterpret_cast<unsigned long long *> (tickets) + SORT_OR_SLOT);
   radix_bins_kernel<<<n_pass, RADIX, 0, st>>> (hist, bins);
 
   static bool configured = false;   // benign race: the attribute is idempotent

@@ -362,13 +362,11 @@ setop2_stream_kernel (const TileArgs args)
       }
       __syncwarp ();
     }
-    if ((args.debug & 2) && lane == 0) {          // experiments: look-back latency statistics in the unused totals rows
-      unsigned long long *row = args.hdr->totals[(args.stream0 + 1) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
-      atomicAdd (row, stats.cycles);
-      atomicAdd (row + 1, stats.polls);
-      row = args.hdr->totals[(args.stream0 + 2) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
-      atomicAdd (row, stats.hops);
-      atomicAdd (row + 1, stats.calls);
+    if ((args.debug & 2) && lane == 0) {          // experiments: look-back latency statistics
+      atomicAdd (&args.hdr->dbg[0], stats.cycles);
+      atomicAdd (&args.hdr->dbg[1], stats.polls);
+      atomicAdd (&args.hdr->dbg[2], stats.hops);
+      atomicAdd (&args.hdr->dbg[3], stats.calls);
     }
     return;
   }
@@ -529,13 +527,10 @@ setop2_stream_kernel (const TileArgs args)
     if (prof) { const long long c5 = clock64 (); t_scan += c4 - c3; t_scatter += c5 - c4; }
     if (++s == STAGES) { s = 0; ph ^= 1u; }
   }
-  if (prof && lane == 0) {       // experiments: per-phase cycles of the consumer warps in the unused totals rows
-    unsigned long long *row = args.hdr->totals[(stream + 1) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
-    atomicAdd (row, (unsigned long long) t_wait); atomicAdd (row + 1, (unsigned long long) t_search);
-    row = args.hdr->totals[(stream + 2) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
-    atomicAdd (row, (unsigned long long) t_merge); atomicAdd (row + 1, (unsigned long long) t_scan);
-    row = args.hdr->totals[(stream + 3) & 3][blockIdx.x & (TOTAL_SLOTS - 1)];
-    atomicAdd (row, (unsigned long long) t_scatter); atomicAdd (row + 1, (unsigned long long) n_tiles_done);
+  if (prof && lane == 0) {       // experiments: per-phase cycles of the consumer warps
+    atomicAdd (&args.hdr->dbg[0], (unsigned long long) t_wait); atomicAdd (&args.hdr->dbg[1], (unsigned long long) t_search);
+    atomicAdd (&args.hdr->dbg[4], (unsigned long long) t_merge); atomicAdd (&args.hdr->dbg[5], (unsigned long long) t_scan);
+    atomicAdd (&args.hdr->dbg[6], (unsigned long long) t_scatter); atomicAdd (&args.hdr->dbg[7], (unsigned long long) n_tiles_done);
   }
 
   // header totals: one pair of atomics per CTA

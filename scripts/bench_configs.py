@@ -11,7 +11,7 @@ import torch
 import genometester4_b200 as g
 from genometester4_b200 import synth
 
-PEAK = 6549.1
+PEAK = json.load(open(Path(__file__).resolve().parent.parent / 'MEASURED_PEAKS.json'))['hbm_gbs'] if (Path(__file__).resolve().parent.parent / 'MEASURED_PEAKS.json').exists() else 6541.5
 g.init(0)
 g.set_stream(torch.cuda.current_stream().cuda_stream)
 which = sys.argv[1:] or ["3", "4", "5"]
@@ -70,11 +70,17 @@ if "5" in which:   # config 5: 8-list union (MakeUnion.pl equivalent), 8 x 5e8 o
             keep.append((wa, ca))
             lists.append(g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), wa.numel(), 32))
         n_in = sum(len(l) for l in lists)
-        for co in (0, 1):
-            r, p_ms, m_ms = timed(lambda: g.union_multi(lists, cutoff=1, countonly=co), reps=3)
-            b = 12 * n_in + (0 if co else 12 * r.n_words)
-            emit(config=5, what="8-list union (tree of two-list merges)", countonly=co, n_each=int(n_each), n_in=n_in, n_out=r.n_words,
-                 kernels_ms=round(p_ms + m_ms, 3), gbs_algorithmic=round(b / (p_ms + m_ms) / 1e6, 1), frac=round(b / (p_ms + m_ms) / 1e6 / PEAK, 3))
-            del r
+        for kway, what in ((1, "8-list union, single-pass k-way kernel"), (0, "8-list union, tree of two-list merges")):
+            g.set_option("use_kway", kway)
+            for op, fn in (("union", g.union_multi), ("intersect", g.intersect_multi)):
+                for co in (0, 1):
+                    r, p_ms, m_ms = timed(lambda: fn(lists, cutoff=1, countonly=co), reps=3)
+                    b = 12 * n_in + (0 if co else 12 * r.n_words)
+                    emit(config=5, what=what, op=op, countonly=co, n_each=int(n_each), n_in=n_in, n_out=r.n_words,
+                         prepass_ms=round(p_ms, 3), merge_ms=round(m_ms, 3), kernels_ms=round(p_ms + m_ms, 3),
+                         gbs_algorithmic=round(b / (p_ms + m_ms) / 1e6, 1), frac=round(b / (p_ms + m_ms) / 1e6 / PEAK, 3),
+                         frac_merge_kernel=round(b / max(m_ms, 1e-6) / 1e6 / PEAK, 3))
+                    del r
+        g.set_option("use_kway", 1)
         del lists, keep
         torch.cuda.empty_cache()
