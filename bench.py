@@ -44,7 +44,9 @@ def parse_args():
     ap.add_argument("--op", choices=["union", "intersect", "diff"], default="union")
     ap.add_argument("--cutoff", type=int, default=1)
     ap.add_argument("--count-only", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (0: --steps, at most 20)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations (3, 4, 5, sharded files)")
+    ap.add_argument("--configs-scale", type=float, default=1.0, help="shrink the extra configurations (debugging)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=1e8, help="k-mers per list of the CPU baseline sample")
@@ -195,9 +197,13 @@ def time_oracle_port(paths, op: str, cutoff: int) -> float:
 OP_FLAG = {"union": "-u", "intersect": "-i", "diff": "-d"}
 
 
-def cpu_arm(n_per_list: float, overlap: float, k: int, op: str, cutoff: int, count_only: bool, repeats: int, warmup: int):
-    """Times the reference's CPU implementation on a bounded sample.  Returns (best k-mers/s, info dict, all times)."""
+def cpu_arm(n_per_list: float, overlap: float, k: int, op: str, cutoff: int, count_only: bool, repeats: int, warmup: int, parity_with=None):
+    """Times the reference's CPU implementation on a bounded sample.  Returns (input k-mers, all times, info dict).
+    parity_with: callable (path_a, path_b) -> bytes of the list file the GPU path produces for the same inputs; when
+    given (and the reference binary wrote a file) the two are compared byte for byte and the verdict is returned in info."""
+    import hashlib
     shm = Path("/dev/shm") if Path("/dev/shm").is_dir() else None
+    parity = None
     with tempfile.TemporaryDirectory(dir=shm) as td:
         td = Path(td)
         paths, n_in = build_sample_lists(td, n_per_list, overlap, k)
@@ -208,12 +214,24 @@ def cpu_arm(n_per_list: float, overlap: float, k: int, op: str, cutoff: int, cou
             if it >= warmup:
                 times.append(t)
         best = min(times)
+        if parity_with is not None and kind == "reference" and not count_only:
+            tag = {"union": "union", "intersect": "intrsec", "diff": "0_diff1"}[op]
+            ref_file = td / f"ref_{k}_{tag}.list"
+            ref_bytes = ref_file.read_bytes()
+            ours = parity_with(paths[0], paths[1])
+            parity = {"records": int(n_in), "output_records": (len(ref_bytes) - 48) // 12,
+                      "reference_sha256": hashlib.sha256(ref_bytes).hexdigest(), "gt4gpu_sha256": hashlib.sha256(ours).hexdigest(),
+                      "identical": ref_bytes == ours,
+                      "what": f"unmodified glistcompare {OP_FLAG[op]} -c {cutoff} vs gt4gpu on the same two {n_in // 2}-k-mer list files, whole output file"}
+            del ref_bytes, ours
     info = {"value": n_in / best, "unit": UNIT, "kind": kind,
             "cores": 3 if kind == "reference" else 1,
             "sample": (f"{OP_FLAG[op]}{' --count_only' if count_only else ''} of the first {n_in} k-mers of the workload "
                        f"({n_in // 2} per list, page-cache-hot .list files in /dev/shm, best of {len(times)}); "
                        + ("unmodified glistcompare from oracle/_ref: 1 merge thread + 2 mmap scout threads (the reference has no multi-threaded merge)"
                           if kind == "reference" else "oracle C port, 1 thread"))}
+    if parity is not None:
+        info["parity_check"] = parity
     return n_in, times, info
 
 
@@ -221,13 +239,14 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    ref_warmup = min(args.warmup, 1)          # one untimed run pages the sample files in; more would only repeat it
     n_in, times, info = cpu_arm(args.ref_sample, args.overlap, args.k, args.op, args.cutoff, args.count_only,
-                                repeats=args.steps, warmup=min(args.warmup, 1))
+                                repeats=args.steps, warmup=ref_warmup)
     ms = 1000.0 * sum(times) / len(times)
     value = n_in / (ms / 1000.0)
     info["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": ref_warmup, "warmup_requested": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 keys / u32 counts", "data": "synthetic",
             "config": workload_config(args, n_in // 2, n_in // 2, sample=True),
             "cpu_baseline": info,
@@ -377,27 +396,320 @@ def run_gt4gpu_arm(args):
 
     # ---- end to end through the C ABI with HOST buffers (packed 12-byte records, pinned), copies timed
     e2e = None
+    host_ceiling = None
     if not args.no_e2e:
+        host_ceiling = measure_host_ceiling(torch, dist, world)
         e2e = run_e2e(args, g, api, torch, dist, world, rank, la, lb, wa, ca, wb, cb, na, nb, n_out, cap)
+        if e2e and host_ceiling:
+            # full duplex: a step cannot be shorter than its larger direction at the measured concurrent rate
+            floor_s = max(e2e["h2d_bytes_per_step"] * world / (host_ceiling["h2d_gbs_concurrent"] * 1e9),
+                          e2e["d2h_bytes_per_step"] * world / (host_ceiling["d2h_gbs_concurrent"] * 1e9))
+            e2e["host_ceiling"] = host_ceiling
+            e2e["frac_of_host_ceiling"] = floor_s / (e2e["ms_per_step"] / 1000.0)
+
+    # the headline lists are no longer needed: give their HBM to the other configurations
+    del la, lb, wa, ca, wb, cb, res
+    if not args.count_only:
+        del ow, oc
+    out_buffers = None
+    torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        def gpu_list_bytes(path_a, path_b):
+            a, b = g.WordList.open(path_a), g.WordList.open(path_b)
+            r = g.compare_wordmaps(a, b, cutoff=args.cutoff, **kw)[stream_name]
+            return r.list_bytes()
         try:
-            _, _, cpu = cpu_arm(args.cpu_sample, args.overlap, args.k, args.op, args.cutoff, args.count_only, repeats=1, warmup=0)
+            _, _, cpu = cpu_arm(args.cpu_sample, args.overlap, args.k, args.op, args.cutoff, args.count_only, repeats=1, warmup=0,
+                                parity_with=gpu_list_bytes)
         except Exception as exc:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(exc)}
+    parity = cpu.pop("parity_check", None) if isinstance(cpu, dict) else None
+
+    configs = None
+    if not args.no_configs:
+        configs = run_other_configs(args, g, api, synth, torch, dist, world, rank, peaks()[0])
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64 keys / u32 counts (integer compare, add mod 2^32)", "data": "synthetic",
                 "config": workload_config(args, na, nb), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": launches, "clocks": clocks,
+                "gpu_launches": launches, "clocks": clocks, "parity_check": parity,
                 "output_kmers": total_out, "input_kmers": total_in, "numa_node_rank0": numa_node, "kernel_config": {"kernel": kernel_name, "stream_shape": args.stream_shape or os.environ.get("GT4GPU_STREAM_SHAPE", "512x9"),
-                                  "tile": args.tile or os.environ.get("GT4GPU_TILE", "256x9")}}
+                                  "tile": args.tile or os.environ.get("GT4GPU_TILE", "256x9")},
+                "configs": configs}
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["identical"]:
+            raise SystemExit("bench.py: the GPU output differs from the reference's on the parity sample")
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_host_ceiling(torch, dist, world, nbytes=1 << 30, reps=3):
+    """What the host can feed: pinned host <-> device copies of 1 GiB on every rank at once, each direction alone and
+    both together (the e2e path overlaps them).  Returns aggregate GB/s over all ranks (slowest rank's time)."""
+    host_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dev_in = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dev_out = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def timed(do_in, do_out):
+        best = None
+        for _ in range(reps + 1):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if do_in:
+                with torch.cuda.stream(s1):
+                    dev_in.copy_(host_in, non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s2):
+                    host_out.copy_(dev_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            best = dt if best is None else min(best, dt)
+        return world * nbytes / best / 1e9
+
+    out = {"h2d_gbs_alone": timed(True, False), "d2h_gbs_alone": timed(False, True)}
+    both = timed(True, True)
+    out["h2d_gbs_concurrent"] = both
+    out["d2h_gbs_concurrent"] = both
+    out["what"] = f"{world} rank(s) x 1 GiB pinned host <-> device copies at once, aggregate GB/s per direction (best of {reps})"
+    del host_in, host_out, dev_in, dev_out
+    return out
+
+
+def run_other_configs(args, g, api, synth, torch, dist, world, rank, peak):
+    """The other BASELINE.json configurations, device resident, STRONG scaling (the global lists are fixed; rank r
+    generates and merges the r-th key range, which is what the splitters hand out), plus the real file -> file sharded path
+    (splitter planning, range loads, merge, all-gather, parallel pwrite) on list files in /dev/shm."""
+    scale = args.configs_scale
+    out = {}
+    gather = torch.zeros(world, 2, dtype=torch.int64, device="cuda") if world > 1 else None
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps=3, warm=1):
+        """ms per call (CUDA events around `reps` calls, max over ranks), kernel ms of the last call, last result."""
+        r = None
+        for _ in range(warm):
+            del r                     # (hand the previous result's buffers back to the pool before the next call needs them)
+            r = fn()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for _ in range(reps):
+            del r
+            r = fn()
+            if world > 1:
+                mine = torch.tensor([r.n_words, r.total_count], dtype=torch.int64, device="cuda")
+                dist.all_gather_into_tensor(gather.view(-1), mine)
+        ev1.record()
+        sync_all()
+        p_ms, m_ms, _ = g.last_timing()
+        t = torch.tensor([ev0.elapsed_time(ev1) / reps, p_ms + m_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), r
+
+    def total(x):
+        t = torch.tensor([x], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def entry(what, n_in, n_out, ms, kernel_ms, countonly, **extra):
+        b = 12 * n_in + (0 if countonly else 12 * n_out)
+        e = {"what": what, "scaling": "strong", "input_kmers": n_in, "output_kmers": n_out, "ms_per_step": ms, "kernels_ms": kernel_ms,
+             "kmers_per_s": n_in / (ms / 1e3), "algorithmic_gb": b / 1e9, "frac_of_aggregate_hbm_peak": b / (ms / 1e3) / 1e9 / (peak * world)}
+        e.update(extra)
+        return e
+
+    def pair_shard(k, n_a, n_b, n_both, seed=42):
+        m = int(n_a + n_b - n_both)
+        u0, u1 = m * rank // world, m * (rank + 1) // world
+        (wa, ca), (wb, cb) = synth.pair_torch(seed, k, m, u0, u1, (n_a - n_both) / m, (n_b - n_both) / m)
+        la = g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), wa.numel(), k, keepalive=(wa, ca))
+        lb = g.WordList.from_device(wb.data_ptr(), cb.data_ptr(), wb.numel(), k, keepalive=(wb, cb))
+        return la, lb
+
+    # ---- configs[1], the other operations on the headline lists (per-GPU weak-scaling shards as in the headline)
+    n1 = args.n_per_list * scale
+    m_local, pa, pb = universe_for(n1, args.overlap)
+    (wa, ca), (wb, cb) = synth.pair_torch(42, args.k, m_local * world, rank * m_local, (rank + 1) * m_local, pa, pb)
+    la = g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), wa.numel(), args.k, keepalive=(wa, ca))
+    lb = g.WordList.from_device(wb.data_ptr(), cb.data_ptr(), wb.numel(), args.k, keepalive=(wb, cb))
+    for name, kw, stream in (("2_intersect", dict(find_intrsec=1), "intrsec"), ("2_diff", dict(find_diff=1), "diff1"),
+                             ("2_union_intersect_diff", dict(find_union=1, find_intrsec=1, find_diff=1), None)):
+        def run():
+            r = g.compare_wordmaps(la, lb, cutoff=args.cutoff, **kw)
+            return r[stream] if stream else r["union"]
+        ms, kms, r = timed(run)
+        n_in = total(len(la) + len(lb))
+        if stream:
+            n_out = total(r.n_words)
+        else:
+            rr = g.compare_wordmaps(la, lb, cutoff=args.cutoff, **kw)
+            n_out = total(sum(x.n_words for x in rr.values()))
+            del rr
+        out[name] = entry(f"glistcompare {' '.join('-' + c for c in ('u' if 'find_union' in kw else '') + ('i' if 'find_intrsec' in kw else '') + ('d' if 'find_diff' in kw else ''))} "
+                          f"on the headline lists ({n1:.0e} k-mers per list per GPU, weak scaling)", n_in, n_out, ms, kms, False, scaling="weak")
+        del r
+    del la, lb, wa, ca, wb, cb
+    torch.cuda.empty_cache()
+
+    # ---- configs[2]: glistcompare -d -c 5, 32-mers, 3e9 / 1e9 k-mers, key-range sharded over the GPUs
+    la, lb = pair_shard(32, 3e9 * scale, 1e9 * scale, 0.8e9 * scale)
+    for co in (0, 1):
+        ms, kms, r = timed(lambda: g.compare_wordmaps(la, lb, find_diff=1, cutoff=5, countonly=co)["diff1"])
+        out["3" + ("_count_only" if co else "")] = entry(
+            f"glistcompare -d -c 5{' --count_only' if co else ''}, 32-mers, {3e9 * scale:.0e} / {1e9 * scale:.0e} k-mers, key-range sharded over {world} GPU(s)",
+            total(len(la) + len(lb)), total(r.n_words), ms, kms, bool(co))
+        del r
+    del la, lb
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: counts-only intersect / union sweep
+    sweep = []
+    for n, ovs in ((1e6, (0.01, 0.5, 0.99)), (1e7, (0.5,)), (1e8, (0.01, 0.5, 0.99)), (1e9, (0.5,)), (3e9, (0.01, 0.5, 0.99))):
+        n = n * scale
+        for ov in ovs:
+            la, lb = pair_shard(25, n, n, ov * n)
+            for op, kw, stream in (("intersect", dict(find_intrsec=1), "intrsec"), ("union", dict(find_union=1), "union")):
+                ms, kms, r = timed(lambda: g.compare_wordmaps(la, lb, countonly=1, **kw)[stream], reps=3 if n >= 1e8 else 10)
+                e = entry(f"--count_only {op}", total(len(la) + len(lb)), total(r.n_words), ms, kms, True, n_per_list=int(n), overlap=ov, op=op)
+                del e["what"]
+                sweep.append(e)
+                del r
+            del la, lb
+            torch.cuda.empty_cache()
+    out["4"] = {"what": f"counts-only intersect / union sweep, 25-mers, lists key-range sharded over {world} GPU(s)", "points": sweep}
+
+    # ---- configs[4]: union of 8 lists of 5e8 32-mers drawn from one universe (MakeUnion.pl), single-pass k-way kernel
+    n_each = int(5e8 * scale)
+    m = n_each * 3
+    u0, u1 = m * rank // world, m * (rank + 1) // world
+    lists, keep = [], []
+    for j in range(8):
+        w, c = synth.list_torch(5, 32, m, u0, u1, j, 1 / 3)
+        keep.append((w, c))
+        lists.append(g.WordList.from_device(w.data_ptr(), c.data_ptr(), w.numel(), 32))
+    n_in = total(sum(len(x) for x in lists))
+    for name, fn in (("5", g.union_multi), ("5_intersect", g.intersect_multi)):
+        for co in (0, 1):
+            ms, kms, r = timed(lambda: fn(lists, cutoff=1, countonly=co), reps=2)
+            out[name + ("_count_only" if co else "")] = entry(
+                f"{'union' if fn is g.union_multi else 'intersection'} of 8 lists of {n_each:.0e} 32-mers{' --count_only' if co else ''} (single-pass k-way kernel), key-range sharded over {world} GPU(s)",
+                n_in, total(r.n_words), ms, kms, bool(co))
+            del r
+    del lists, keep
+    torch.cuda.empty_cache()
+
+    # ---- the real sharded file path (genometester4_b200/sharded.py) on config-3 shaped list files in /dev/shm
+    try:
+        out["sharded_files"] = run_sharded_files(args, g, api, synth, torch, dist, world, rank, scale)
+    except Exception as exc:  # pragma: no cover
+        out["sharded_files"] = {"error": repr(exc)}
+    return out
+
+
+def run_sharded_files(args, g, api, synth, torch, dist, world, rank, scale):
+    """glistcompare -d -c 5 of two 32-mer list FILES (3e8 / 1e8 k-mers, a tenth of configs[2]) through
+    sharded.compare_files: host-side splitter planning on the mmaps, every rank loads its record range, merges, the
+    ranks all-gather {n_out, sum}, every rank pwrites its slice of the output file.  Whole call timed per phase."""
+    import hashlib
+    import shutil
+
+    import numpy as np
+
+    from genometester4_b200 import sharded
+    n_a, n_b, n_both, k = int(3e8 * scale), int(1e8 * scale), int(0.8e8 * scale), 32
+    shm = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path(tempfile.gettempdir())
+    td = shm / "gt4gpu_bench_sharded"
+    if rank == 0:
+        shutil.rmtree(td, ignore_errors=True)
+        td.mkdir(parents=True)
+        m = n_a + n_b - n_both
+        (wa, ca), (wb, cb) = synth.pair_torch(7, k, m, 0, m, (n_a - n_both) / m, (n_b - n_both) / m)
+        for name, w, c in (("A", wa, ca), ("B", wb, cb)):
+            n = w.numel()
+            dev = torch.empty(n * 12, dtype=torch.uint8, device="cuda")
+            assert api._lib.load().gt4gpu_interleave(w.data_ptr(), c.data_ptr(), n, dev.data_ptr()) == 0
+            rec = dev.cpu().numpy()
+            hdr = np.zeros(1, dtype=[("code", "<u4"), ("major", "<u4"), ("minor", "<u4"), ("k", "<u4"), ("n", "<u8"),
+                                     ("total", "<u8"), ("start", "<u8"), ("wb", "<u4"), ("cb", "<u4")])
+            hdr["code"], hdr["major"], hdr["minor"], hdr["k"] = 0x47543443, 4, 2, k
+            hdr["n"], hdr["total"], hdr["start"], hdr["wb"], hdr["cb"] = n, int(c.to(torch.int64).sum().item()), 48, 8, 4
+            with open(td / f"{name}.list", "wb") as f:
+                f.write(hdr.tobytes())
+                rec.tofile(f)
+            del dev, rec
+        del wa, ca, wb, cb
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    best, phases_best, tot = None, None, None
+    for it in range(3):
+        timings = {}
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tot = sharded.compare_files(td / "A.list", td / "B.list", str(td / "out"), find_diff=1, cutoff=5, timings=timings)
+        dt = time.perf_counter() - t0
+        names = ["plan", "load", "merge", "exchange", "write"]
+        t = torch.tensor([dt] + [timings.get(x, 0.0) for x in names], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if best is None or float(t[0]) < best:
+            best = float(t[0])
+            phases_best = {x: float(t[i + 1]) for i, x in enumerate(names)}
+    res = None
+    if rank == 0:
+        out_file = td / f"out_{k}_0_diff1.list"
+        sha = hashlib.sha256()
+        with open(out_file, "rb") as f:
+            while True:
+                blk = f.read(1 << 26)
+                if not blk:
+                    break
+                sha.update(blk)
+        res = {"what": f"sharded.compare_files: glistcompare -d -c 5 of two 32-mer list files ({n_a} / {n_b} k-mers) in /dev/shm, {world} rank(s): "
+                       "splitter planning, range loads (H2D), merge, all-gather of output counts, parallel pwrite; best of 3, phases = slowest rank",
+               "input_kmers": n_a + n_b, "output_kmers": tot["diff1"][0], "seconds": best, "kmers_per_s": (n_a + n_b) / best,
+               "phase_seconds": phases_best, "output_sha256": sha.hexdigest(),
+               "bytes_in_plus_out": 12 * (n_a + n_b + tot["diff1"][0])}
+        exe = reference_binary()
+        if world == 1 and exe is not None and scale == 1.0:
+            # the unmodified reference on the very same files: byte-for-byte parity at 4e8 input k-mers
+            t0 = time.perf_counter()
+            subprocess.run([str(exe), str(td / "A.list"), str(td / "B.list"), "-d", "-c", "5", "-o", str(td / "ref")], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            res["reference_seconds"] = time.perf_counter() - t0
+            ref_sha = hashlib.sha256()
+            with open(td / f"ref_{k}_0_diff1.list", "rb") as f:
+                while True:
+                    blk = f.read(1 << 26)
+                    if not blk:
+                        break
+                    ref_sha.update(blk)
+            res["reference_sha256"] = ref_sha.hexdigest()
+            res["identical_to_reference"] = ref_sha.hexdigest() == sha.hexdigest()
+        shutil.rmtree(td, ignore_errors=True)
+    if world > 1:
+        dist.barrier()
+    return res
 
 
 def run_e2e(args, g, api, torch, dist, world, rank, la, lb, wa, ca, wb, cb, na, nb, n_out, cap):
@@ -443,15 +755,16 @@ def run_e2e(args, g, api, torch, dist, world, rank, la, lb, wa, ca, wb, cb, na, 
                                              countonly=int(args.count_only), out_records=outs)
         return n_o[sidx]
 
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, 20)
     one()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         e_out = one()
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / args.e2e_steps
+    dt = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     tot = torch.tensor([ea + eb], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -459,7 +772,7 @@ def run_e2e(args, g, api, torch, dist, world, rank, la, lb, wa, ca, wb, cb, na, 
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dt = float(t.item())
     return {"value": int(tot.item()) / dt, "unit": UNIT, "h2d_bytes_per_step": 12 * (ea + eb),
-            "d2h_bytes_per_step": 0 if args.count_only else 12 * int(e_out), "ms_per_step": dt * 1000.0, "steps": args.e2e_steps,
+            "d2h_bytes_per_step": 0 if args.count_only else 12 * int(e_out), "ms_per_step": dt * 1000.0, "steps": e2e_steps,
             "api": "gt4gpu_compare2_host_aos (packed 12-byte records in pinned host memory in and out)",
             "sample_fraction_of_workload": frac}
 

@@ -101,6 +101,41 @@ int ensure_ready ()
   return gt4gpu_init (-1);
 }
 
+// Pinned bounce buffers for the file <-> device paths.  cudaMallocHost costs tens of milliseconds per call (it pins pages),
+// so the buffers are kept and handed out again; concurrent callers each get their own.
+constexpr size_t BOUNCE_BYTES = (8ull << 20) * 12;      // 8 Mi records
+struct PinnedPool {
+  std::mutex mutex;
+  std::vector<void *> free_list;
+  void *take ()
+  {
+    {
+      std::lock_guard<std::mutex> lock (mutex);
+      if (!free_list.empty ()) {
+        void *p = free_list.back ();
+        free_list.pop_back ();
+        return p;
+      }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost (&p, BOUNCE_BYTES) != cudaSuccess) { cudaGetLastError (); return nullptr; }
+    return p;
+  }
+  void give (void *p)
+  {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock (mutex);
+    free_list.push_back (p);
+  }
+  void release_all ()
+  {
+    std::lock_guard<std::mutex> lock (mutex);
+    for (void *p : free_list) cudaFreeHost (p);
+    free_list.clear ();
+  }
+};
+PinnedPool g_pinned;
+
 int dev_alloc (void **p, size_t bytes)
 {
   CU (cudaMallocAsync (p, bytes ? bytes : 16, g_ctx.stream));
@@ -457,7 +492,7 @@ int upload_aos (const void *records, uint64_t n, uint64_t *d_words, uint32_t *d_
     int rc = 0;
     for (int b = 0; b < 2 && !rc; b++) {
       rc = dev_alloc (&stage[b], chunk * 12);
-      if (!rc && cudaMallocHost (&bounce[b], chunk * 12) != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "cudaMallocHost failed");
+      if (!rc && !(bounce[b] = g_pinned.take ())) rc = fail (GT4GPU_ERR_CUDA, "cudaMallocHost failed");
       if (!rc && cudaEventCreateWithFlags (&done_ev[b], cudaEventDisableTiming) != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "cudaEventCreate failed");
     }
     const unsigned n_threads = std::min (8u, std::max (2u, std::thread::hardware_concurrency () / 2));
@@ -474,7 +509,7 @@ int upload_aos (const void *records, uint64_t n, uint64_t *d_words, uint32_t *d_
     if (e == cudaSuccess) e = cudaStreamSynchronize (g_ctx.stream);
     for (int k = 0; k < 2; k++) {
       dev_free (stage[k]);
-      if (bounce[k]) cudaFreeHost (bounce[k]);
+      g_pinned.give (bounce[k]);
       if (done_ev[k]) cudaEventDestroy (done_ev[k]);
     }
     if (rc) return rc;
@@ -512,7 +547,7 @@ int download_aos (const uint64_t *d_words, const uint32_t *d_counts, uint64_t n,
   cudaEvent_t ready[2] = {nullptr, nullptr};
   for (int b = 0; b < 2 && !rc; b++) {
     rc = dev_alloc (&stage[b], chunk * 12);
-    if (!rc && cudaMallocHost (&pinned[b], chunk * 12) != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "cudaMallocHost failed");
+    if (!rc && !(pinned[b] = g_pinned.take ())) rc = fail (GT4GPU_ERR_CUDA, "cudaMallocHost failed");
     if (!rc && cudaEventCreateWithFlags (&ready[b], cudaEventDisableTiming) != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "cudaEventCreate failed");
   }
   auto enqueue = [&] (uint64_t done, int b) {
@@ -533,7 +568,7 @@ int download_aos (const uint64_t *d_words, const uint32_t *d_counts, uint64_t n,
   cudaStreamSynchronize (g_ctx.stream);
   for (int k = 0; k < 2; k++) {
     dev_free (stage[k]);
-    if (pinned[k]) cudaFreeHost (pinned[k]);
+    g_pinned.give (pinned[k]);
     if (ready[k]) cudaEventDestroy (ready[k]);
   }
   if (!rc && e != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "download: %s", cudaGetErrorString (e));
@@ -920,6 +955,7 @@ void gt4gpu_shutdown (void)
   std::lock_guard<std::mutex> lock (g_init_mutex);
   if (!g_ctx.ready) return;
   cudaStreamSynchronize (g_ctx.stream);
+  g_pinned.release_all ();
   if (g_ctx.own_stream) cudaStreamDestroy (g_ctx.own_stream);
   if (g_ctx.in_stream) cudaStreamDestroy (g_ctx.in_stream);
   if (g_ctx.out_stream) cudaStreamDestroy (g_ctx.out_stream);

@@ -5,6 +5,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// The store warps read a stage with ordinary (generic-proxy) loads and hand it back to the producer through an mbarrier;
+// the producer then lets the TMA (async proxy) overwrite it.  GT4_STORE_FENCE = 1 (default) puts the proxy fence into
+// the store warps, after their last read of the stage; 0 puts it into the producer, right before the TMA copies.
+// Measured: no difference (10.65 vs 10.69 ms on the headline merge, profiles/r02_stream_variants.txt).
+#ifndef GT4_STORE_FENCE
+#define GT4_STORE_FENCE 1
+#endif
+
 namespace gt4gpu {
 namespace dev {
 

@@ -181,6 +181,9 @@ kway_tile_kernel (const KwayArgs args)
         }
       }
       mbar_wait_sleep (&bar_empty[s], ph ^ 1u, 200);
+#if !GT4_STORE_FENCE
+      fence_proxy_async ();      // the stage's last generic-proxy accesses (observed through bar_empty) before the TMA writes
+#endif
       if (tile >= n_tiles) {
         // END marker through every stage under the normal protocol (see setop2_stream_kernel)
         if (lane == 0) {
@@ -206,7 +209,7 @@ kway_tile_kernel (const KwayArgs args)
         total = 0;
       }
       const int pc = (int) (c_lo & 3u);                             // count phase inside its 16-byte group
-      const int width = n ? ((pc + n + 3) & ~3) : 0;
+      const int width = (lane < NL) ? ((pc + n + 1 + 3) & ~3) : 0;  // + 1: the slot behind the slice holds a sentinel key
       int incl = width;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -332,7 +335,9 @@ kway_tile_kernel (const KwayArgs args)
       } else if (st_tid == 0) {
         args.hdr->overflow = 1u;
       }
+#if GT4_STORE_FENCE
       fence_proxy_async ();
+#endif
       __syncwarp ();
       if (lane == 0) mbar_arrive (&bar_empty[s]);
       if (++s == S) { s = 0; ph ^= 1u; }
@@ -376,16 +381,22 @@ kway_tile_kernel (const KwayArgs args)
     const uint64_t tile_id = m.tile;
 
     // ---- (1) how many records of every slice fall into every bucket?  (hist is all zero between tiles)
-    int base[NL];
+    int base[NL], nj[NL];
+    int n_max = 0;
 #pragma unroll
     for (int j = 0; j < NL; j++) {
-      const int nj = m.n[j];
+      nj[j] = m.n[j];
       base[j] = m.idx0[j];
-      uint32_t *hj = hist + j * NB;
-      for (int i = tid; i < nj; i += NC) {
-        const uint64_t k = sk[base[j] + i];
-        if (i > 0 && !(sk[base[j] + i - 1] < k)) args.hdr->overflow = 2u;      // not strictly ascending: reported, result undefined
-        atomicAdd (&hj[kw_bucket<BSH> (k, lo, lsh, mult, NB)], 1u);
+      n_max = nj[j] > n_max ? nj[j] : n_max;
+    }
+    // a key larger than any other behind every slice: a list that runs out inside the merge loop below then shows a head
+    // that can never be the smallest (the word after a thread's share of a slice is a natural sentinel: it belongs to a
+    // later bucket, so it is larger than every word of this bucket)
+    if (tid < NL) sk[m.idx0[tid] + m.n[tid]] = ~0ull;
+    for (int i = tid; i < n_max; i += NC) {
+#pragma unroll
+      for (int j = 0; j < NL; j++) {
+        if (i < nj[j]) atomicAdd (&hist[j * NB + kw_bucket<BSH> (sk[base[j] + i], lo, lsh, mult, NB)], 1u);
       }
     }
     consumer_sync<NC> ();
@@ -436,7 +447,7 @@ kway_tile_kernel (const KwayArgs args)
       end[j] = idx[j] + (int) hcnt[j];
       sparse_off += excl_j;
       remaining += (int) hcnt[j];
-      head[j] = (idx[j] < end[j]) ? sk[idx[j]] : ~0ull;
+      head[j] = sk[idx[j]];
     }
     int pos = sparse_off;
     while (remaining > 0) {
@@ -445,14 +456,20 @@ kway_tile_kernel (const KwayArgs args)
       for (int j = 1; j < NL; j++) mn = head[j] < mn ? head[j] : mn;
       uint32_t f = 0;
       int n_hit = 0;
+      // straight-line code on purpose: every list looks at its count and reloads its head whether it holds the word or not
+      // (the loads are cheap, eight divergent branches per word are not)
 #pragma unroll
       for (int j = 0; j < NL; j++) {
-        if (idx[j] < end[j] && head[j] == mn) {
-          f = kw_fold<MODE> (f, sc[idx[j]], n_hit == 0, rule);
-          n_hit += 1;
-          idx[j] += 1;
-          head[j] = (idx[j] < end[j]) ? sk[idx[j]] : ~0ull;
-        }
+        const bool hit = head[j] == mn && idx[j] < end[j];
+        const uint32_t c = sc[idx[j]];
+        f = hit ? kw_fold<MODE> (f, c, n_hit == 0, rule) : f;
+        n_hit += hit ? 1 : 0;
+        idx[j] += hit ? 1 : 0;
+        head[j] = sk[idx[j]];
+      }
+      if (n_hit == 0) {               // only lists that are not sorted get here: report, never spin
+        args.hdr->overflow = 2u;
+        break;
       }
       remaining -= n_hit;
       if (MODE == KWAY_MODE_GENERIC && rule == RULE_NUMBER) f = args.count_override;

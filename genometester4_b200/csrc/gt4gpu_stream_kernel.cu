@@ -213,6 +213,9 @@ setop2_stream_kernel (const TileArgs args)
         prefetch_l2 (args.b_counts + pb_lo, (pb_hi - pb_lo) * 4);
       }
       mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
+#if !GT4_STORE_FENCE
+      fence_proxy_async ();      // the stage's last generic-proxy accesses (observed through bar_empty) before the TMA writes
+#endif
       if (tile >= n_tiles) {
         // out of work: send an END marker through EVERY stage, in order and under the normal stage protocol
         // (each look-back warp owns one stage and must see its own marker; a barrier may never be advanced
@@ -413,7 +416,9 @@ setop2_stream_kernel (const TileArgs args)
       } else if (st_tid == 0) {
         args.hdr->overflow = 1u;
       }
+#if GT4_STORE_FENCE
       fence_proxy_async ();          // generic accesses to the stage before the async proxy (TMA) refills it
+#endif
       __syncwarp ();
       if (lane == 0) mbar_arrive (&bar_empty[s]);
       if (++s == STAGES) { s = 0; ph ^= 1u; }

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from pathlib import Path
 
 import numpy as np
@@ -57,14 +58,18 @@ def plan(paths, n_parts: int, stream: bool = False):
     return headers, bounds, splitters
 
 
-def _gpu_merge_pair(paths, ranges, k, kwargs, stream):
+def _gpu_merge_pair(paths, ranges, k, kwargs, stream, phases=None):
     la = api.WordList.open(paths[0], stream=stream, first=ranges[0][0], count=ranges[0][1] - ranges[0][0])
     lb = api.WordList.open(paths[1], stream=stream, first=ranges[1][0], count=ranges[1][1] - ranges[1][0])
+    if phases is not None:
+        phases.mark("load")
     return api.compare_wordmaps(la, lb, **kwargs)
 
 
-def _gpu_merge_multi(paths, ranges, k, kwargs, stream):
+def _gpu_merge_multi(paths, ranges, k, kwargs, stream, phases=None):
     lists = [api.WordList.open(p, stream=stream, first=r[0], count=r[1] - r[0]) for p, r in zip(paths, ranges)]
+    if phases is not None:
+        phases.mark("load")
     op = kwargs.pop("op")
     fn = api.union_multi if op == "union" else api.intersect_multi
     return {("union" if op == "union" else "intrsec"): fn(lists, **kwargs)}
@@ -137,31 +142,53 @@ def _local_totals(results):
     return out
 
 
+class _Phases:
+    """Wall-clock seconds of the phases of one sharded call on this rank (plan / load / merge / exchange / write)."""
+
+    def __init__(self, sink):
+        self.sink, self.t = sink, time.perf_counter()
+
+    def mark(self, name):
+        if self.sink is not None:
+            now = time.perf_counter()
+            self.sink[name] = self.sink.get(name, 0.0) + (now - self.t)
+            self.t = now
+
+
 def compare_files(path_a, path_b, out_prefix="out", *, find_union=0, find_intrsec=0, find_diff=0, find_ddiff=0, subtract=0,
-                  countonly=0, cutoff=1, rule=api.RULE_DEFAULT, count_override=1, stream=False, merge_fn=None, mode=0o666):
-    """Sharded `glistcompare A B ...` (two lists).  Returns {stream: (n_words, total_count)} (global)."""
+                  countonly=0, cutoff=1, rule=api.RULE_DEFAULT, count_override=1, stream=False, merge_fn=None, mode=0o666,
+                  timings=None):
+    """Sharded `glistcompare A B ...` (two lists).  Returns {stream: (n_words, total_count)} (global).
+    timings: optional dict that receives this rank's seconds per phase."""
     _, rank, world = _dist()
+    ph = _Phases(timings)
     paths = [Path(path_a), Path(path_b)]
     headers, bounds, _ = plan(paths, world, stream)
+    ph.mark("plan")
     if headers[0].word_length != headers[1].word_length:
         raise ValueError(f"File {path_b} has different word length ({headers[1].word_length} != {headers[0].word_length})")
     k = headers[0].word_length
     ranges = [(int(bounds[j, rank]), int(bounds[j, rank + 1])) for j in range(2)]
     kwargs = dict(find_union=find_union, find_intrsec=find_intrsec, find_diff=find_diff, find_ddiff=find_ddiff, subtract=subtract,
                   countonly=countonly, cutoff=cutoff, rule=rule, count_override=count_override)
-    results = (merge_fn or _gpu_merge_pair)(paths, ranges, k, kwargs, stream)
+    results = _gpu_merge_pair(paths, ranges, k, kwargs, stream, ph) if merge_fn is None else merge_fn(paths, ranges, k, kwargs, stream)
+    ph.mark("merge")
     streams = [s for s in api.STREAM_NAMES if s in results]
     totals = _exchange(_local_totals(results), streams)
+    ph.mark("exchange")
     _assemble(out_prefix, k, streams, results, totals, countonly, mode)
+    ph.mark("write")
     return {s: (totals[s][1], totals[s][2]) for s in streams}
 
 
 def multi_files(paths, out_prefix="out", *, op="union", countonly=0, cutoff=1, rule=api.RULE_DEFAULT, count_override=1,
-                stream=False, merge_fn=None, mode=0o644):
+                stream=False, merge_fn=None, mode=0o644, timings=None):
     """Sharded `glistcompare L0 L1 L2 ... -u|-i` (N lists).  Returns {stream: (n_words, total_count)}."""
     _, rank, world = _dist()
+    ph = _Phases(timings)
     paths = [Path(p) for p in paths]
     headers, bounds, _ = plan(paths, world, stream)
+    ph.mark("plan")
     # header word length as in the reference: first non-empty list for the union (glistcompare.c:535), list 0 for the intersection (:639)
     k = headers[0].word_length
     if op == "union":
@@ -171,8 +198,11 @@ def multi_files(paths, out_prefix="out", *, op="union", countonly=0, cutoff=1, r
         # an empty list anywhere empties the intersection (:631-636); a rank whose RANGE of some list is empty is not that
         ranges = [(0, 0)] * len(paths)
     kwargs = dict(op=op, cutoff=cutoff, rule=rule, count_override=count_override, countonly=countonly)
-    results = (merge_fn or _gpu_merge_multi)(paths, ranges, k, kwargs, stream)
+    results = _gpu_merge_multi(paths, ranges, k, kwargs, stream, ph) if merge_fn is None else merge_fn(paths, ranges, k, kwargs, stream)
+    ph.mark("merge")
     streams = list(results)
     totals = _exchange(_local_totals(results), streams)
+    ph.mark("exchange")
     _assemble(out_prefix, k, streams, results, totals, countonly, mode)
+    ph.mark("write")
     return {s: (totals[s][1], totals[s][2]) for s in streams}
