@@ -69,7 +69,7 @@ struct Context {
   int stream_consumers = 512;   // consumer threads per CTA of the single-output kernel (setop2_stream_kernel)
   int stream_items = 9;         // its merged items per thread
   int use_stream = 1;           // 0: run single-output merges through setop2_tile_kernel too
-  int use_kway = 1;             // 0: N-list calls go through the tree / chain of two-list merges
+  int use_kway = 1;             // 0: N-list calls go through the tree / chain of two-list merges; 1: unions take the single pass; 2: intersections too
   int sm_count = 0;
 };
 Context g_ctx;
@@ -939,7 +939,7 @@ int gt4gpu_init (int device)
   env = getenv ("GT4GPU_USE_STREAM_KERNEL");
   if (env) g_ctx.use_stream = atoi (env) != 0;
   env = getenv ("GT4GPU_USE_KWAY");
-  if (env) g_ctx.use_kway = atoi (env) != 0;
+  if (env) g_ctx.use_kway = atoi (env) < 0 ? 0 : atoi (env) > 2 ? 2 : atoi (env);
   env = getenv ("GT4GPU_TILE");   // multi-output kernel, e.g. GT4GPU_TILE=256x11
   if (env) {
     int nt = 0, vt = 0;
@@ -999,8 +999,8 @@ int gt4gpu_set_option (const char *name, int value)
     g_ctx.stream_consumers = value;
     return 0;
   }
-  if (!strcmp (name, "use_kway")) {            // 0: N-list calls run as a tree / chain of two-list merges
-    g_ctx.use_kway = value != 0;
+  if (!strcmp (name, "use_kway")) {            // 0: N-list calls run as a tree / chain of two-list merges; 1: unions take the single pass; 2: intersections too
+    g_ctx.use_kway = value < 0 ? 0 : value > 2 ? 2 : value;
     return 0;
   }
   if (!strcmp (name, "use_stream_kernel")) {
@@ -1259,7 +1259,10 @@ int gt4gpu_intersect_multi (const gt4gpu_list *const *lists, unsigned n_lists, u
     fill_result (out, mo[0], k, countonly != 0);
     return 0;
   }
-  if (g_ctx.use_kway && n_lists >= 3) {
+  // The chain below already reads every list once and its intermediates only shrink, so its traffic is the algorithmic
+  // one; measured on 8 lists sharing a third of a universe it beats the single pass (2.8 vs 4.7 ms, profiles/
+  // r02_config5_one_gpu.jsonl).  The single pass is kept selectable (use_kway = 2) and tested.
+  if (g_ctx.use_kway >= 2 && n_lists >= 3) {
     std::vector<DevList> all;
     for (unsigned j = 0; j < n_lists; j++) all.push_back (DevList{lists[j]->words, lists[j]->counts, lists[j]->n_words});
     MergeOut root;

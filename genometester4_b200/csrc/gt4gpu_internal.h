@@ -69,7 +69,14 @@ cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items
 // ---- single-pass N-list union / intersection (gt4gpu_kway_kernel.cu)
 static constexpr int KWAY_MAX_LISTS = 8;        // lists per pass (their heads live in registers); more lists go through several passes
 static constexpr int KWAY_SAMPLE = 128;         // every KWAY_SAMPLE-th word of every list is a boundary candidate
-static constexpr int KWAY_TILE_CAP = 4096;      // records a tile can hold
+#ifndef GT4_KWAY_CAP
+#define GT4_KWAY_CAP 4096
+#endif
+#ifndef GT4_KWAY_STAGES
+#define GT4_KWAY_STAGES 3
+#endif
+static constexpr int KWAY_TILE_CAP = GT4_KWAY_CAP;      // records a tile can hold
+static constexpr int KWAY_STAGES = GT4_KWAY_STAGES;     // tiles in flight per CTA (shared memory: stages + one scratch buffer)
 static constexpr int KWAY_CONSUMERS = 256;
 enum KwayMode : int { KWAY_MODE_GENERIC = 0, KWAY_MODE_U_ADD = 1, KWAY_MODE_I_MIN = 2 };
 

@@ -57,7 +57,7 @@ struct KwayCfg {
   static constexpr int SLOTS = KWAY_TILE_CAP + 8 * NL + 8;
   static constexpr size_t STAGE_BYTES = (size_t) SLOTS * 12;
   static constexpr size_t SPARSE_BYTES = (size_t) KWAY_TILE_CAP * 12;
-  static constexpr size_t HIST_BYTES = (size_t) NL * NB * 4;      // records of every slice in every bucket
+  static constexpr size_t HIST_BYTES = (size_t) (NL * NB + 32) * 4;     // records of every slice in every bucket (+ one dummy bucket per lane)
   static constexpr size_t SMEM_BYTES = S * STAGE_BYTES + SPARSE_BYTES + HIST_BYTES;
   static constexpr int LOG2_NB = NB == 128 ? 7 : NB == 256 ? 8 : 9;
   static constexpr int BUCKET_SHIFT = 30 - LOG2_NB;               // bucket = umulhi (u, mult) >> BUCKET_SHIFT, mult < 2^32
@@ -169,18 +169,23 @@ kway_tile_kernel (const KwayArgs args)
     uint32_t ph = 0;
     while (true) {
       // this tile's slice of every list (lane j < NL) and its key range (lane 0); loaded before the wait
-      uint64_t c_lo = 0, c_hi = 0, k_lo = 0, k_hi = 0;
+      uint64_t c_lo = 0, c_hi = 0, k_lo = 0, k_hi = 0, p_lo = 0, p_hi = 0;
+      const uint64_t pf_tile = tile + gridDim.x;       // about what this CTA will claim next: its slices are prefetched into L2
       if (tile < n_tiles) {
         if (lane < NL) {
           c_lo = args.cuts[tile * NL + lane];
           c_hi = args.cuts[(tile + 1) * NL + lane];
+          if (!COUNT_ONLY && pf_tile < n_tiles) {
+            p_lo = args.cuts[pf_tile * NL + lane];
+            p_hi = args.cuts[(pf_tile + 1) * NL + lane];
+          }
         }
         if (lane == 0) {
           k_lo = args.bounds[tile];
           k_hi = args.bounds[tile + 1];
         }
       }
-      mbar_wait_sleep (&bar_empty[s], ph ^ 1u, 200);
+      mbar_wait_sleep (&bar_empty[s], ph ^ 1u, 50);
 #if !GT4_STORE_FENCE
       fence_proxy_async ();      // the stage's last generic-proxy accesses (observed through bar_empty) before the TMA writes
 #endif
@@ -270,6 +275,11 @@ kway_tile_kernel (const KwayArgs args)
       if (lane == 0) mbar_arrive_expect_tx (&bar_full[s], tx);
       __syncwarp ();
       if (tma_bytes) bulk_g2s (tma_dst, tma_src, tma_bytes, &bar_full[s]);
+      // (measured: halves the time the consumers wait for a stage; the count-only pass is faster without it)
+      if (!COUNT_ONLY && lane < NL && p_hi > p_lo && p_hi - p_lo <= (uint64_t) KWAY_TILE_CAP && p_hi <= args.n[lane]) {
+        prefetch_l2 (args.words[lane] + p_lo, (p_hi - p_lo) * 8);
+        prefetch_l2 (args.counts[lane] + p_lo, (p_hi - p_lo) * 4);
+      }
       if (lane == 0) tile = atomicAdd (&args.hdr->ticket, 1u);
       tile = __shfl_sync (0xffffffffu, tile, 0);
       if (++s == S) { s = 0; ph ^= 1u; }
@@ -393,11 +403,17 @@ kway_tile_kernel (const KwayArgs args)
     // that can never be the smallest (the word after a thread's share of a slice is a natural sentinel: it belongs to a
     // later bucket, so it is larger than every word of this bucket)
     if (tid < NL) sk[m.idx0[tid] + m.n[tid]] = ~0ull;
+    // (all loads of a round first, then all atomics: the compiler must keep shared-memory loads behind earlier shared
+    // atomics; lanes beyond the end of a slice count into a dummy bucket of their own instead of branching)
     for (int i = tid; i < n_max; i += NC) {
+      uint64_t k[NL];
+      unsigned b[NL];
 #pragma unroll
-      for (int j = 0; j < NL; j++) {
-        if (i < nj[j]) atomicAdd (&hist[j * NB + kw_bucket<BSH> (sk[base[j] + i], lo, lsh, mult, NB)], 1u);
-      }
+      for (int j = 0; j < NL; j++) k[j] = sk[base[j] + (i < nj[j] ? i : 0)];
+#pragma unroll
+      for (int j = 0; j < NL; j++) b[j] = (i < nj[j]) ? j * NB + kw_bucket<BSH> (k[j], lo, lsh, mult, NB) : NL * NB + lane;
+#pragma unroll
+      for (int j = 0; j < NL; j++) atomicAdd (&hist[b[j]], 1u);
     }
     consumer_sync<NC> ();
 
@@ -522,9 +538,22 @@ kway_tile_kernel (const KwayArgs args)
     }
     const long long c4 = prof ? clock64 () : 0;
     const int dst = warp_prefix + incl - cnt;
-    for (int q = 0; q < cnt; q++) {
-      sk[dst + q] = sparse_k[sparse_off + q];
-      sc[dst + q] = sparse_c[sparse_off + q];
+    for (int q = 0; q < cnt; q += 4) {           // four independent copies in flight, the last round predicated
+      uint64_t k4[4];
+      uint32_t c4[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int src = sparse_off + (q + r < cnt ? q + r : q);
+        k4[r] = sparse_k[src];
+        c4[r] = sparse_c[src];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (q + r < cnt) {
+          sk[dst + q + r] = k4[r];
+          sc[dst + q + r] = c4[r];
+        }
+      }
     }
     __syncwarp ();
     if (lane == 0) mbar_arrive (&bar_comp[s]);
@@ -671,15 +700,14 @@ cudaError_t launch_kway_tiles (const KwayArgs &args, int nl, bool count_only, in
   const int mode = kway_select_mode (args.op, args.rule);
   static int consumers = 0;      // benign race: idempotent
   if (consumers == 0) {
-    const char *env = getenv ("GT4GPU_KWAY_CONSUMERS");          // experiments: 128 / 256 / 512 consumer threads (8-list variant)
+    const char *env = getenv ("GT4GPU_KWAY_CONSUMERS");          // experiments: 256 / 512 consumer threads (8-list variant)
     const int v = env ? atoi (env) : KWAY_CONSUMERS;
-    consumers = (v == 128 || v == 512) ? v : KWAY_CONSUMERS;
+    consumers = (v == 512) ? v : KWAY_CONSUMERS;
   }
-  if (nl <= 4) return launch_kway_mode<4, KWAY_CONSUMERS, 3> (args, mode, count_only, sm_count, st);
+  if (nl <= 4) return launch_kway_mode<4, KWAY_CONSUMERS, KWAY_STAGES> (args, mode, count_only, sm_count, st);
   if (nl <= 8) {
-    if (consumers == 128) return launch_kway_mode<8, 128, 3> (args, mode, count_only, sm_count, st);
-    if (consumers == 512) return launch_kway_mode<8, 512, 3> (args, mode, count_only, sm_count, st);
-    return launch_kway_mode<8, KWAY_CONSUMERS, 3> (args, mode, count_only, sm_count, st);
+    if (consumers == 512) return launch_kway_mode<8, 512, KWAY_STAGES> (args, mode, count_only, sm_count, st);
+    return launch_kway_mode<8, KWAY_CONSUMERS, KWAY_STAGES> (args, mode, count_only, sm_count, st);
   }
   return cudaErrorInvalidValue;
 }

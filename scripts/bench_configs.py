@@ -71,7 +71,7 @@ if "5" in which:   # config 5: 8-list union (MakeUnion.pl equivalent), 8 x 5e8 o
             lists.append(g.WordList.from_device(wa.data_ptr(), ca.data_ptr(), wa.numel(), 32))
         n_in = sum(len(l) for l in lists)
         for kway, what in ((1, "8-list union, single-pass k-way kernel"), (0, "8-list union, tree of two-list merges")):
-            g.set_option("use_kway", kway)
+            g.set_option("use_kway", 2 if kway else 0)
             for op, fn in (("union", g.union_multi), ("intersect", g.intersect_multi)):
                 for co in (0, 1):
                     r, p_ms, m_ms = timed(lambda: fn(lists, cutoff=1, countonly=co), reps=3)

@@ -12,6 +12,7 @@ op = sys.argv[3] if len(sys.argv) > 3 else "union"
 co = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 g.init(0); g.set_stream(torch.cuda.current_stream().cuda_stream)
+g.set_option("use_kway", 2)
 m = n_each * 3
 lists, keep = [], []
 for j in range(n_lists):

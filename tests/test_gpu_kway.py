@@ -15,7 +15,9 @@ pytestmark = pytest.mark.gpu
 def g():
     import genometester4_b200 as g
     g.init(0)
-    return g
+    g.set_option("use_kway", 2)        # unions AND intersections through the single-pass kernel (the default keeps the chain for intersections)
+    yield g
+    g.set_option("use_kway", 1)
 
 
 def _check_all(g, oracle, lists, k, rules_u=("default", "max", "add"), rules_i=("default", "max", "add"), cutoffs=(1, 40), tag=""):
@@ -60,7 +62,7 @@ def test_kway_equals_the_tree_it_replaces(g):
         tree_u = g.union_multi(gl, cutoff=3).to_host()
         tree_i = g.intersect_multi(gl, cutoff=1).to_host()
     finally:
-        g.set_option("use_kway", 1)
+        g.set_option("use_kway", 2)
     kway_u = g.union_multi(gl, cutoff=3).to_host()
     kway_i = g.intersect_multi(gl, cutoff=1).to_host()
     for a, b in ((tree_u, kway_u), (tree_i, kway_i)):
@@ -180,7 +182,7 @@ def test_kway_large_shared_universe_properties(g):
         ut = g.union_multi(lists, cutoff=5)
         it = g.intersect_multi(lists, cutoff=0)
     finally:
-        g.set_option("use_kway", 1)
+        g.set_option("use_kway", 2)
     uk = g.union_multi(lists, cutoff=5)
     for a, b in ((ut, uk), (it, i)):
         assert (a.n_words, a.total_count) == (b.n_words, b.total_count)
