@@ -69,6 +69,7 @@ struct Context {
   int stream_consumers = 512;   // consumer threads per CTA of the single-output kernel (setop2_stream_kernel)
   int stream_items = 9;         // its merged items per thread
   int use_stream = 1;           // 0: run single-output merges through setop2_tile_kernel too
+  int use_fused = 1;            // 0: several outputs of one merge take one pass of the single-output kernel each
   int use_kway = 1;             // 0: N-list calls go through the tree / chain of two-list merges; 1: unions take the single pass; 2: intersections too
   int sm_count = 0;
 };
@@ -185,8 +186,11 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   // (measured, profiles/README.md), so the fused kernel is only used when the stream kernel is switched off.
   const TileShape shape = g_ctx.shape;
   const bool use_stream = g_ctx.use_stream != 0;
+  // several outputs: ONE pass of the fused kernel (one read of the lists); -du and count-only runs take one pass per output
+  const bool use_fused = use_stream && g_ctx.use_fused && !countonly && fused_applicable (p, stream_mask);
   const int ns = (n_req == 1 || use_stream) ? 1 : 4;
-  const uint64_t tile = use_stream ? (uint64_t) g_ctx.stream_consumers * g_ctx.stream_items : (uint64_t) shape.threads * shape.items;
+  const uint64_t tile = use_fused ? (uint64_t) fused_tile_slots (stream_mask)
+                      : use_stream ? (uint64_t) g_ctx.stream_consumers * g_ctx.stream_items : (uint64_t) shape.threads * shape.items;
   const uint64_t n_tiles = (total + tile - 1) / tile;
   cudaStream_t st = g_ctx.stream;
 
@@ -208,7 +212,7 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
 
   // scratch: [CallHeader | descriptors | partition]
   const size_t hdr_bytes = (sizeof (CallHeader) + 255) & ~(size_t) 255;
-  const size_t desc_bytes = countonly ? 0 : (size_t) ns * n_tiles * sizeof (uint64_t);
+  const size_t desc_bytes = countonly ? 0 : use_fused ? fused_desc_bytes (n_tiles) : (size_t) ns * n_tiles * sizeof (uint64_t);
   const size_t part_bytes = (n_tiles + 1) * sizeof (uint64_t);
   unsigned char *ws = nullptr;
   int rc = dev_alloc ((void **) &ws, hdr_bytes + desc_bytes + part_bytes);
@@ -243,7 +247,10 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
   CU (launch_partition (a.words, a.n, b.words, b.n, (uint32_t) tile, n_tiles, part, st));
   CU (cudaEventRecord (tl_ev[1], st));
   uint32_t n_launches = 1;
-  if (use_stream) {
+  if (use_fused) {
+    CU (launch_setop2_fused (args, g_ctx.sm_count, st));
+    n_launches += 1;
+  } else if (use_stream) {
     bool first = true;
     for (int s = 0; s < 4; s++) {
       if (!((stream_mask >> s) & 1u)) continue;
@@ -1001,6 +1008,10 @@ int gt4gpu_set_option (const char *name, int value)
   }
   if (!strcmp (name, "use_kway")) {            // 0: N-list calls run as a tree / chain of two-list merges; 1: unions take the single pass; 2: intersections too
     g_ctx.use_kway = value < 0 ? 0 : value > 2 ? 2 : value;
+    return 0;
+  }
+  if (!strcmp (name, "use_fused")) {
+    g_ctx.use_fused = value != 0;
     return 0;
   }
   if (!strcmp (name, "use_stream_kernel")) {

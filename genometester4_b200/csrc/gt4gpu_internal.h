@@ -66,6 +66,14 @@ cudaError_t launch_setop2 (const TileArgs &args, TileShape shape, int n_streams,
 bool stream_shape_supported (int consumers, int items);
 cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items, bool count_only, int sm_count, cudaStream_t st);
 
+// multi-output kernel on the same pipeline (gt4gpu_fused_kernel.cu): one read of the lists, up to four outputs.
+// Applies to two or more outputs without -du; its tiles (fused_tile_slots) differ from the single-output kernel's, and its
+// look-back descriptors are 32 bytes per tile (fused_desc_bytes).
+bool fused_applicable (const SetOpParams &p, uint32_t ops);
+uint32_t fused_tile_slots (uint32_t ops);
+size_t fused_desc_bytes (uint64_t n_tiles);
+cudaError_t launch_setop2_fused (const TileArgs &args, int sm_count, cudaStream_t st);
+
 // ---- single-pass N-list union / intersection (gt4gpu_kway_kernel.cu)
 static constexpr int KWAY_MAX_LISTS = 8;        // lists per pass (their heads live in registers); more lists go through several passes
 static constexpr int KWAY_SAMPLE = 128;         // every KWAY_SAMPLE-th word of every list is a boundary candidate
