@@ -88,6 +88,9 @@ SIGNATURES = {
     "gt4gpu_result_free": (None, [C.POINTER(CResult)]),
     "gt4gpu_compare2_host_aos": (_I, [_P, _U64, _P, _U64, _U32, _U32, _I, _U32, _U32, _I, _I,
                                       C.POINTER(_P), C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64)]),
+    "gt4gpu_device_count": (_I, []),
+    "gt4gpu_compare2_files": (_I, [C.c_char_p, C.c_char_p, _I, _U32, _I, _U32, _U32, _I, _I, C.POINTER(_I),
+                                   C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U32)]),
     "gt4gpu_plan_splitters": (_I, [C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(_U64), C.c_uint, C.c_uint,
                                    C.POINTER(_U64), C.POINTER(_U64)]),
     "gt4gpu_deinterleave": (_I, [_P, _U64, _P, _P]),

@@ -408,6 +408,39 @@ def compare2_host_records(rec_a: np.ndarray, rec_b: np.ndarray, word_length: int
     return list(n_out), list(t_out)
 
 
+def compare_files(path_a, path_b, out_prefix: str = "out", find_union=0, find_intrsec=0, find_diff=0, find_ddiff=0, subtract=0, countonly=0,
+                  cutoff: int = 1, rule=RULE_DEFAULT, count_override: int = 1, stream: bool = False, mode: int = 0o666) -> dict:
+    """`glistcompare A B ...` file to file through the pipelined path (gt4gpu_compare2_files): same output names as the
+    reference (`<out>_<k>_union.list`, ..., written through `.tmp` and renamed).  Returns {stream: (n_words, total_count)}."""
+    import os
+    if find_ddiff:
+        find_diff = 1
+    ops = (OP_UNION if find_union else 0) | (OP_INTRSEC if find_intrsec else 0) | (OP_DIFF if find_diff else 0) | (OP_DDIFF if find_ddiff else 0)
+    h = _lib.Header()
+    _check(_lib.load().gt4gpu_list_read_header(os.fsencode(str(path_a)), int(stream), C.byref(h)))
+    k = h.word_length
+    tags = {"union": "union", "intrsec": "intrsec", "diff1": "0_diff1", "diff2": "0_diff2"}
+    fds = (C.c_int * 4)(-1, -1, -1, -1)
+    names = {}
+    try:
+        for s in range(4):
+            if (ops >> s) & 1 and not countonly:
+                final = f"{out_prefix}_{k}_{tags[STREAM_NAMES[s]]}.list"
+                names[s] = (final + ".tmp", final)
+                fds[s] = os.open(names[s][0], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, mode)
+        n_out, tot = (C.c_uint64 * 4)(), (C.c_uint64 * 4)()
+        wl = C.c_uint32(0)
+        _check(_lib.load().gt4gpu_compare2_files(os.fsencode(str(path_a)), os.fsencode(str(path_b)), int(stream), ops, _rule(rule), cutoff,
+                                                 count_override, int(bool(subtract)), int(bool(countonly)), fds, n_out, tot, C.byref(wl)))
+    finally:
+        for s in range(4):
+            if fds[s] >= 0:
+                os.close(fds[s])
+    for tmp, final in names.values():
+        os.rename(tmp, final)
+    return {STREAM_NAMES[s]: (int(n_out[s]), int(tot[s])) for s in range(4) if (ops >> s) & 1}
+
+
 def plan_splitters(key_arrays, n_parts: int):
     """Key-range sharding plan (gt4gpu_plan_splitters).  key_arrays: list of 1-D numpy arrays, either
     u64 keys (stride 8) or packed RECORD arrays (stride 12).  Returns (bounds[n_lists, n_parts+1], splitters)."""

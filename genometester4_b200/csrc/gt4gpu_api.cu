@@ -915,6 +915,13 @@ void gt4gpu_header_init (gt4gpu_header *hdr, uint32_t word_length)
   hdr->count_bytes = 4;
 }
 
+int gt4gpu_device_count (void)
+{
+  int count = 0;
+  if (cudaGetDeviceCount (&count) != cudaSuccess) { cudaGetLastError (); return 0; }
+  return count;
+}
+
 int gt4gpu_init (int device)
 {
   std::lock_guard<std::mutex> lock (g_init_mutex);
@@ -1947,6 +1954,221 @@ int gt4gpu_compare2_host_aos (const void *records_a, uint64_t n_a, const void *r
   return compare2_host_pipelined (static_cast<const unsigned char *> (records_a), n_a, static_cast<const unsigned char *> (records_b), n_b,
                                   word_length, ops, rule, cutoff, count_override, subtract, countonly,
                                   out_records, out_capacity, n_out, total_out, n_parts);
+}
+
+
+// ------------------------------------------------------------------ file-to-file, pipelined
+
+namespace {
+
+// One direction of the file pipeline: records [first, first + n) of a mapped list file -> device AoS buffer, through two
+// pinned bounce buffers (filled by a few threads) so that the copy out of the page cache overlaps the H2D transfer.
+struct FileCopyBuffers {
+  void *pinned[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int init ()
+  {
+    for (int b = 0; b < 2; b++) {
+      if (!(pinned[b] = g_pinned.take ())) return fail (GT4GPU_ERR_CUDA, "cudaMallocHost failed");
+      if (cudaEventCreateWithFlags (&ev[b], cudaEventDisableTiming) != cudaSuccess) return fail (GT4GPU_ERR_CUDA, "cudaEventCreate failed");
+    }
+    return 0;
+  }
+  ~FileCopyBuffers ()
+  {
+    for (int b = 0; b < 2; b++) {
+      g_pinned.give (pinned[b]);
+      if (ev[b]) cudaEventDestroy (ev[b]);
+    }
+  }
+};
+
+constexpr uint64_t FILE_CHUNK = BOUNCE_BYTES / 12;
+
+cudaError_t upload_records (const unsigned char *src, uint64_t n, void *d_aos, uint64_t *d_words, uint32_t *d_counts, FileCopyBuffers &buf,
+                            unsigned n_threads, cudaStream_t st)
+{
+  cudaError_t e = cudaSuccess;
+  int b = 0;
+  for (uint64_t done = 0; done < n && e == cudaSuccess; done += FILE_CHUNK, b ^= 1) {
+    const uint64_t m = std::min (FILE_CHUNK, n - done);
+    if (done >= 2 * FILE_CHUNK) e = cudaEventSynchronize (buf.ev[b]);
+    if (e != cudaSuccess) break;
+    copy_parallel (buf.pinned[b], src + done * 12, m * 12, n_threads);
+    e = cudaMemcpyAsync (static_cast<unsigned char *> (d_aos) + done * 12, buf.pinned[b], m * 12, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord (buf.ev[b], st);
+  }
+  if (e == cudaSuccess && n) e = launch_deinterleave (d_aos, n, d_words, d_counts, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize (st);
+  return e;
+}
+
+// device SoA result -> records in the file at byte offset `at`, chunk i + 1 copied out while chunk i is written
+int download_records (const uint64_t *d_words, const uint32_t *d_counts, uint64_t n, void *d_aos, int fd, int64_t at, FileCopyBuffers &buf, cudaStream_t st)
+{
+  if (n == 0) return 0;
+  cudaError_t e = launch_interleave (d_words, d_counts, n, d_aos, st);
+  auto enqueue = [&] (uint64_t done, int b) {
+    const uint64_t m = std::min (FILE_CHUNK, n - done);
+    e = cudaMemcpyAsync (buf.pinned[b], static_cast<unsigned char *> (d_aos) + done * 12, m * 12, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord (buf.ev[b], st);
+  };
+  int rc = 0, b = 0;
+  if (e == cudaSuccess) enqueue (0, 0);
+  for (uint64_t done = 0; done < n && !rc && e == cudaSuccess; done += FILE_CHUNK, b ^= 1) {
+    if (done + FILE_CHUNK < n) enqueue (done + FILE_CHUNK, b ^ 1);
+    if (e != cudaSuccess) break;
+    e = cudaEventSynchronize (buf.ev[b]);
+    if (e != cudaSuccess) break;
+    rc = write_all (fd, buf.pinned[b], std::min (FILE_CHUNK, n - done) * 12, at + (int64_t) (done * 12));
+  }
+  cudaStreamSynchronize (st);
+  if (!rc && e != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "file output: %s", cudaGetErrorString (e));
+  return rc;
+}
+
+}  // namespace
+
+int gt4gpu_compare2_files (const char *path_a, const char *path_b, int stream_mode, uint32_t ops, int rule, uint32_t cutoff,
+                           uint32_t count_override, int subtract, int countonly, const int out_fd[4],
+                           uint64_t n_out[4], uint64_t total_out[4], uint32_t *word_length)
+{
+  if (!path_a || !path_b || !n_out || !total_out) return fail (GT4GPU_ERR_ARG, "null argument");
+  if (!ops || (ops & ~15u)) return fail (GT4GPU_ERR_ARG, "ops must be a non-empty OR of GT4GPU_OP_*");
+  if (rule < GT4GPU_RULE_DEFAULT || rule > GT4GPU_RULE_NUMBER) return fail (GT4GPU_ERR_ARG, "unknown rule %d", rule);
+  if (!countonly && !out_fd) return fail (GT4GPU_ERR_ARG, "missing output descriptors");
+  Mapping ma, mb;
+  int rc = map_file (path_a, ma);
+  if (!rc) rc = map_file (path_b, mb);
+  if (rc) return rc;
+  if (is_index_file (ma.data, ma.size) || is_index_file (mb.data, mb.size))
+    return fail (GT4GPU_ERR_ARG, "gt4gpu_compare2_files reads list files only (open index files with gt4gpu_list_open)");
+  gt4gpu_header ha, hb;
+  if ((rc = parse_header (ma.data, ma.size, stream_mode, path_a, &ha))) return rc;
+  if ((rc = parse_header (mb.data, mb.size, stream_mode, path_b, &hb))) return rc;
+  if ((rc = ensure_ready ())) return rc;
+  if (word_length) *word_length = ha.word_length;           // output header word length = first list's (src/glistcompare.c:814)
+  const unsigned char *rec_a = ma.data + ha.list_start, *rec_b = mb.data + hb.list_start;
+  const uint64_t n_a = ha.n_words, n_b = hb.n_words, total = n_a + n_b;
+  for (int s = 0; s < 4; s++) n_out[s] = total_out[s] = 0;
+
+  uint64_t part_records = 64ull << 20;
+  if (const char *env = getenv ("GT4GPU_HOST_PART_RECORDS")) part_records = strtoull (env, nullptr, 10);
+  if (part_records < 1024) part_records = 1024;
+  const unsigned n_parts = (unsigned) std::max<uint64_t> (1, std::min<uint64_t> ((total + part_records - 1) / part_records, 1024));
+  std::vector<uint64_t> bounds (2 * (n_parts + 1));
+  {
+    const void *keys[2] = {rec_a, rec_b};
+    const size_t strides[2] = {12, 12};
+    const uint64_t sizes[2] = {n_a, n_b};
+    if ((rc = gt4gpu_plan_splitters (keys, strides, sizes, 2, n_parts, bounds.data (), nullptr))) return rc;
+  }
+  const uint64_t *ba = bounds.data (), *bb = bounds.data () + n_parts + 1;
+  uint64_t max_a = 0, max_b = 0;
+  for (unsigned p = 0; p < n_parts; p++) {
+    max_a = std::max (max_a, ba[p + 1] - ba[p]);
+    max_b = std::max (max_b, bb[p + 1] - bb[p]);
+  }
+  SetOpParams prm;
+  memset (&prm, 0, sizeof (prm));
+  prm.ops = ops; prm.cutoff = cutoff; prm.count_override = count_override; prm.subtract = subtract ? 1 : 0; prm.sem = SEM_PAIR;
+  for (int s = 0; s < 4; s++) prm.rule[s] = resolve_rule (rule, s);
+
+  struct Set {
+    void *aos_a = nullptr, *aos_b = nullptr;
+    uint64_t *wa = nullptr, *wb = nullptr;
+    uint32_t *ca = nullptr, *cb = nullptr;
+    uint64_t *ow[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *oc[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t n[4] = {0, 0, 0, 0};
+  } set[2];
+  void *oaos = nullptr;
+  uint64_t cap[4], cap_max = 0;
+  for (int s = 0; s < 4; s++) { cap[s] = worst_case (prm, s, max_a, max_b); if ((ops >> s) & 1u) cap_max = std::max (cap_max, cap[s]); }
+  auto alloc = [&] (void **p, size_t bytes) { if (!rc) rc = dev_alloc (p, bytes); };
+  for (int b = 0; b < 2; b++) {
+    alloc (&set[b].aos_a, max_a * 12); alloc (&set[b].aos_b, max_b * 12);
+    alloc ((void **) &set[b].wa, max_a * 8); alloc ((void **) &set[b].ca, max_a * 4);
+    alloc ((void **) &set[b].wb, max_b * 8); alloc ((void **) &set[b].cb, max_b * 4);
+    for (int s = 0; s < 4; s++) {
+      if (!((ops >> s) & 1u) || countonly) continue;
+      alloc ((void **) &set[b].ow[s], cap[s] * 8); alloc ((void **) &set[b].oc[s], cap[s] * 4);
+    }
+  }
+  if (!countonly) alloc (&oaos, cap_max * 12);
+  FileCopyBuffers in_buf, out_buf;
+  if (!rc) rc = in_buf.init ();
+  if (!rc && !countonly) rc = out_buf.init ();
+  cudaError_t e = cudaSuccess;
+  if (!rc) e = cudaStreamSynchronize (g_ctx.stream);     // the allocations above are ordered on the compute stream
+
+  const int device = g_ctx.device;
+  const unsigned copy_threads = std::min (8u, std::max (2u, std::thread::hardware_concurrency () / 2));
+  cudaError_t e_up = cudaSuccess;
+  int rc_down = 0;
+  auto upload = [&] (unsigned p) {
+    cudaSetDevice (device);
+    Set &st = set[p & 1];
+    e_up = upload_records (rec_a + ba[p] * 12, ba[p + 1] - ba[p], st.aos_a, st.wa, st.ca, in_buf, copy_threads, g_ctx.in_stream);
+    if (e_up == cudaSuccess) e_up = upload_records (rec_b + bb[p] * 12, bb[p + 1] - bb[p], st.aos_b, st.wb, st.cb, in_buf, copy_threads, g_ctx.in_stream);
+  };
+  uint64_t written[4] = {0, 0, 0, 0};
+  auto download = [&] (unsigned p) {
+    cudaSetDevice (device);
+    Set &st = set[p & 1];
+    for (int s = 0; s < 4 && !rc_down; s++) {
+      if (!((ops >> s) & 1u) || countonly) continue;
+      rc_down = download_records (st.ow[s], st.oc[s], st.n[s], oaos, out_fd[s], (int64_t) (sizeof (gt4gpu_header) + 12 * written[s]), out_buf, g_ctx.out_stream);
+      written[s] += st.n[s];
+    }
+  };
+  float ms_p = 0.f, ms_m = 0.f;
+  uint32_t nl = 0;
+  if (!rc && e == cudaSuccess) { upload (0); e = e_up; }
+  for (unsigned p = 0; p < n_parts && !rc && e == cudaSuccess; p++) {
+    // three things at once: part p + 1 comes in, part p is merged, part p - 1 goes out
+    std::thread t_up, t_down;
+    if (p + 1 < n_parts) t_up = std::thread (upload, p + 1);
+    if (p >= 1 && !countonly) t_down = std::thread (download, p - 1);
+    Set &st = set[p & 1];
+    MergeOut mo[4];
+    for (int s = 0; s < 4; s++) {
+      if (!((ops >> s) & 1u) || countonly) continue;
+      mo[s].caller = true; mo[s].words = st.ow[s]; mo[s].counts = st.oc[s]; mo[s].capacity = cap[s];
+    }
+    reset_timing ();
+    rc = merge2_device (DevList{st.wa, st.ca, ba[p + 1] - ba[p]}, DevList{st.wb, st.cb, bb[p + 1] - bb[p]}, prm, ops, countonly != 0, mo);
+    ms_p += tl_ms_partition; ms_m += tl_ms_merge; nl += tl_launches;
+    for (int s = 0; s < 4 && !rc; s++) {
+      if (!((ops >> s) & 1u)) continue;
+      st.n[s] = mo[s].n;
+      n_out[s] += mo[s].n;
+      total_out[s] += mo[s].sum;
+    }
+    if (t_up.joinable ()) t_up.join ();
+    if (t_down.joinable ()) t_down.join ();
+    if (!rc && rc_down) rc = rc_down;
+    if (e_up != cudaSuccess) e = e_up;
+  }
+  if (!rc && e == cudaSuccess && !countonly) { download (n_parts - 1); rc = rc_down; }
+  for (int b = 0; b < 2; b++) {
+    dev_free (set[b].aos_a); dev_free (set[b].aos_b); dev_free (set[b].wa); dev_free (set[b].ca); dev_free (set[b].wb); dev_free (set[b].cb);
+    for (int s = 0; s < 4; s++) { dev_free (set[b].ow[s]); dev_free (set[b].oc[s]); }
+  }
+  dev_free (oaos);
+  tl_ms_partition = ms_p; tl_ms_merge = ms_m; tl_launches = nl;
+  if (!rc && e != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "file pipeline: %s", cudaGetErrorString (e));
+  if (rc) return rc;
+  // the headers last, like the reference (header with totals rewritten at offset 0, src/glistcompare.c:907-953)
+  for (int s = 0; s < 4 && !countonly; s++) {
+    if (!((ops >> s) & 1u)) continue;
+    gt4gpu_header h;
+    gt4gpu_header_init (&h, ha.word_length);
+    h.n_words = n_out[s];
+    h.total_count = total_out[s];
+    if ((rc = write_all (out_fd[s], &h, sizeof (h), 0))) return rc;
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------ sharding plan (host only)

@@ -104,6 +104,8 @@ typedef struct gt4gpu_result {
 
 /* Binds the calling process to one CUDA device (one process per GPU) and creates the
  * library stream and memory pool.  device < 0: use the current device. */
+/* number of CUDA devices visible to the process (0 without a driver); no context is created */
+int gt4gpu_device_count (void);
 int gt4gpu_init (int device);
 void gt4gpu_shutdown (void);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream) for all launches.  NULL restores the library's own
@@ -242,6 +244,16 @@ int gt4gpu_compare2_host_aos (const void *records_a, uint64_t n_a, const void *r
                               uint32_t count_override, int subtract, int countonly,
                               void *const out_records[4], const uint64_t out_capacity[4],
                               uint64_t n_out[4], uint64_t total_out[4]);
+
+/* File to file: what glistcompare does with two list files (compare_wordmaps over two GT4WordMap / GT4WordListStream
+ * containers, src/glistcompare.c:256-291, 789-955), as a pipeline: the key space is cut into parts, part p + 1 is read
+ * out of the page cache and copied to the device while part p is merged and part p - 1 is written with pwrite.  out_fd[k]
+ * (k = union, intersection, diff1, diff2; only the requested ones are used, ignored when countonly) receives a complete
+ * list file: records at offset 48, the header with the totals last.  List files only (no GT4I index inputs).
+ * n_out / total_out are always filled; *word_length (may be NULL) is the first list's. */
+int gt4gpu_compare2_files (const char *path_a, const char *path_b, int stream_mode, uint32_t ops, int rule, uint32_t cutoff,
+                           uint32_t count_override, int subtract, int countonly, const int out_fd[4],
+                           uint64_t n_out[4], uint64_t total_out[4], uint32_t *word_length);
 
 /* ---- key-range sharding (multi-GPU) ---------------------------- */
 

@@ -135,3 +135,67 @@ def test_config1_fasta_built_lists(tmp_path, oracle):
             assert r.returncode == 0
             outs.append({f.name: f.read_bytes() for f in sorted(run.glob("out_*"))})
         assert outs[0] == outs[1] and len(outs[0]) == len([f for f in flags if f in ("-i", "-u", "-d")])
+
+
+def test_file_pipeline_many_parts_against_oracle(tmp_path, oracle, monkeypatch):
+    """gt4gpu_compare2_files (the path gt4gpu-compare takes for two list files): forced to cut the key space into many
+    parts, every output file byte-identical to what the reference writes; count-only totals; headers of every minor
+    version on the input side."""
+    import numpy as np
+
+    import genometester4_b200 as g
+    from tests.util import make_pair
+    g.init(0)
+    monkeypatch.setenv("GT4GPU_HOST_PART_RECORDS", "50000")
+    a, b = make_pair(91, 400_000, 350_000, 150_000, 25, "tail")
+    pa, pb = tmp_path / "A.list", tmp_path / "B.list"
+    oracle.write_list(pa, a[0], a[1], 25)
+    oracle.write_list(pb, b[0], b[1], 25, minor=0)           # a 4.0 header (40 bytes) on one side
+    sa, sb = oracle.SList(*a, 25), oracle.SList(*b, 25)
+    tags = {"union": "union", "intrsec": "intrsec", "diff1": "0_diff1", "diff2": "0_diff2"}
+    for kw, cutoff in ((dict(find_union=1), 1), (dict(find_intrsec=1, find_diff=1), 3), (dict(find_union=1, find_intrsec=1, find_diff=1, find_ddiff=1), 2),
+                       (dict(find_diff=1, subtract=1), 1)):
+        okw = dict(union=bool(kw.get("find_union")), intrsec=bool(kw.get("find_intrsec")), diff=bool(kw.get("find_diff")), ddiff=bool(kw.get("find_ddiff")),
+                   subtract=bool(kw.get("subtract")))
+        want = oracle.compare2(sa, sb, cutoff=cutoff, **okw)
+        tot = g.api.compare_files(pa, pb, str(tmp_path / "o"), cutoff=cutoff, **kw)
+        assert sorted(tot) == sorted(want)
+        for s, r in want.items():
+            assert tot[s] == (r.n_words, r.total_count), (kw, s)
+            assert (tmp_path / f"o_25_{tags[s]}.list").read_bytes() == refrun.list_bytes(r, 25), (kw, s)
+            (tmp_path / f"o_25_{tags[s]}.list").unlink()
+        co = g.api.compare_files(pa, pb, str(tmp_path / "o"), cutoff=cutoff, countonly=1, **kw)
+        assert co == tot and not list(tmp_path.glob("o_25_*"))
+    # an empty list on either side, and a single part
+    pe = tmp_path / "E.list"
+    oracle.write_list(pe, np.zeros(0, np.uint64), np.zeros(0, np.uint32), 25)
+    monkeypatch.setenv("GT4GPU_HOST_PART_RECORDS", "100000000")
+    for x, y, sx, sy in ((pa, pe, sa, None), (pe, pb, None, sb), (pa, pb, sa, sb)):
+        ex = sx or oracle.SList(np.zeros(0, np.uint64), np.zeros(0, np.uint32), 25)
+        ey = sy or oracle.SList(np.zeros(0, np.uint64), np.zeros(0, np.uint32), 25)
+        want = oracle.compare2(ex, ey, union=True, diff=True, cutoff=1)
+        tot = g.api.compare_files(x, y, str(tmp_path / "e"), find_union=1, find_diff=1, cutoff=1)
+        for s, r in want.items():
+            assert tot[s] == (r.n_words, r.total_count)
+            assert (tmp_path / f"e_25_{tags[s]}.list").read_bytes() == refrun.list_bytes(r, 25)
+
+
+def test_cli_gpus_n_matches_one_process(inputs, tmp_path):
+    """gt4gpu-compare --gpus N (one process per key-range shard, offsets exchanged over pipes, parallel pwrite): the files,
+    stdout and exit status of the one-process run, for two-list and N-list modes.  On a one-GPU box the shards share it."""
+    d, pair_paths, multi_paths = inputs
+    jobs = [(pair_paths["p_tail"], ["-u", "-i", "-dd", "-c", "2"]), (pair_paths["p_small"], ["-du", "-i"]), (pair_paths["p_extremes"], ["-u", "-d"]),
+            (pair_paths["p_a_empty"], ["-u", "-d"]), (multi_paths["m8_tail"], ["-u", "-i", "-c", "2"]), (multi_paths["m4_one_empty"], ["-u"]),
+            (multi_paths["m3_small"], ["-u", "-i", "-r", "min"]), (multi_paths["m4_huge"], ["-u", "-r", "max"])]
+    for n_gpus in (2, 3):
+        for paths, flags in (jobs if n_gpus == 2 else jobs[:1] + jobs[4:5]):       # (every process start pays a CUDA context)
+            outs = {}
+            for tag, extra in (("one", []), ("many", ["--gpus", str(n_gpus)])):
+                run = tmp_path / f"{tag}_{n_gpus}"
+                run.mkdir(exist_ok=True)
+                for f in run.glob("out_*"):
+                    f.unlink()
+                r = run_cli([*paths, *flags, *extra], run)
+                rc = run_cli([*paths, *flags, "--count_only", *extra], run)
+                outs[tag] = (r.returncode, _collect(run), rc.returncode, rc.stdout)
+            assert outs["one"] == outs["many"], (n_gpus, flags)
