@@ -285,9 +285,10 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
     fprintf (stderr, "gt4gpu debug: look-backs %llu, mean %.0f cycles, %.2f polls, %.2f extra hops\n", h.dbg[3],
              (double) h.dbg[0] / h.dbg[3], (double) h.dbg[1] / h.dbg[3], (double) h.dbg[2] / h.dbg[3] - 1.0);
   if ((args.debug & 32) && h.dbg[7])
-    fprintf (stderr, "gt4gpu debug: consumer warp cycles per tile: wait %.0f search %.0f merge %.0f scan+barrier %.0f scatter %.0f (warp-tiles %llu)\n",
+    fprintf (stderr, "gt4gpu debug: consumer warp cycles per tile: wait %.0f search %.0f merge %.0f scan+barrier %.0f scatter %.0f (warp-tiles %llu); "
+                     "splitter warp per tile: waits for the TMA %.0f, searches %.0f\n",
              (double) h.dbg[0] / h.dbg[7], (double) h.dbg[1] / h.dbg[7], (double) h.dbg[4] / h.dbg[7], (double) h.dbg[5] / h.dbg[7],
-             (double) h.dbg[6] / h.dbg[7], h.dbg[7]);
+             (double) h.dbg[6] / h.dbg[7], h.dbg[7], (double) h.dbg[2] / n_tiles, (double) h.dbg[3] / n_tiles);
   if (h.overflow == 2u) return fail (GT4GPU_ERR_ARG, "input lists are not strictly ascending (the merge result is undefined)");
   if (h.overflow) return fail (GT4GPU_ERR_CAPACITY, "output buffer too small for the merge result");
   for (int s = 0; s < 4; s++) {
@@ -602,12 +603,12 @@ static int write_span (int fd, const unsigned char *p, size_t bytes, int64_t off
 int write_all (int fd, const void *buf, size_t bytes, int64_t offset)
 {
   const unsigned char *p = static_cast<const unsigned char *> (buf);
-  constexpr size_t PARALLEL_MIN = 64u << 20;
-  constexpr unsigned N_THREADS = 4;
+  constexpr size_t PARALLEL_MIN = 32u << 20;
+  constexpr unsigned N_THREADS = 8;       // (page-cache / tmpfs writes are bound by page allocation per thread: 4 -> 8 threads measured)
   if (bytes >= PARALLEL_MIN) {
     const int64_t at = (offset >= 0) ? offset : (int64_t) lseek (fd, 0, SEEK_CUR);
     if (at >= 0) {
-      int err[N_THREADS] = {0, 0, 0, 0};
+      int err[N_THREADS] = {};
       std::vector<std::thread> pool;
       const size_t piece = ((bytes / N_THREADS) + 4095) & ~(size_t) 4095;
       for (unsigned t = 0; t < N_THREADS; t++) {
@@ -2103,7 +2104,7 @@ int gt4gpu_compare2_files (const char *path_a, const char *path_b, int stream_mo
   if (!rc) e = cudaStreamSynchronize (g_ctx.stream);     // the allocations above are ordered on the compute stream
 
   const int device = g_ctx.device;
-  const unsigned copy_threads = std::min (8u, std::max (2u, std::thread::hardware_concurrency () / 2));
+  const unsigned copy_threads = std::min (16u, std::max (2u, std::thread::hardware_concurrency () / 2));
   cudaError_t e_up = cudaSuccess;
   int rc_down = 0;
   auto upload = [&] (unsigned p) {

@@ -261,4 +261,48 @@ GT4_UNROLL
   }
 }
 
+// The same for a thread whose VT slots all lie inside the tile, when the tile is staged with the element of A before
+// it (ka[-1]), the element of A after it (ka[na]) and the element of B after it (kb[nb]).  Those neighbours are natural
+// sentinels: tile boundaries are merge-path co-ranks with ties taking A first, so A[a_hi] > every B of the tile and
+// B[b_hi] >= every A of the tile, and no cursor needs a bound.  A slot is reported one step late, when the following
+// slot has been looked at: the B half of a pair is loaded anyway (it is the next slot) and brings the pair's second
+// count, so only a pair in the thread's LAST slot costs a load of its own.
+template <int VT, typename Sink>
+GT4_HD void merge_slots_interior (const uint64_t *ka, const uint32_t *ca, const uint64_t *kb, const uint32_t *cb,
+                                  int i0, int d0, Sink &&sink)
+{
+  const uint64_t *pa = ka + i0, *pb = kb + (d0 - i0);
+  const uint32_t *pca = ca + i0, *pcb = cb + (d0 - i0);
+  uint64_t key_a = *pa;
+  uint64_t key_b = *pb;
+  bool live = pa[-1] != key_b;      // else the first slot is the B half of a pair reported by the previous thread (or tile)
+  uint64_t key_prev = 0;
+  uint32_t cnt_prev = 0;
+  bool a_prev = false, pair_prev = false, live_prev = false;
+GT4_UNROLL
+  for (int s = 0; s < VT; s++) {
+    const bool take_a = key_a <= key_b;
+    const bool pair = key_a == key_b;
+    const uint32_t cnt = *(take_a ? pca : pcb);
+    if (s > 0) sink (s - 1, key_prev, cnt_prev, a_prev ? (pair_prev ? cnt : 0u) : cnt_prev, a_prev, !a_prev || pair_prev, live_prev);
+    key_prev = take_a ? key_a : key_b;
+    cnt_prev = cnt;
+    a_prev = take_a;
+    pair_prev = pair;
+    live_prev = live;
+    live = !pair;                   // the slot after a pair is its B half
+    if (take_a) {
+      pa += 1;
+      pca += 1;
+      key_a = *pa;
+    } else {
+      pb += 1;
+      pcb += 1;
+      key_b = *pb;
+    }
+  }
+  const uint32_t cnt_last = pair_prev ? *pcb : 0u;
+  sink (VT - 1, key_prev, cnt_prev, a_prev ? cnt_last : cnt_prev, a_prev, !a_prev || pair_prev, live_prev);
+}
+
 }  // namespace gt4gpu

@@ -42,7 +42,28 @@ namespace {
 #ifndef GT4_STORE_WARPS
 #define GT4_STORE_WARPS 2
 #endif
+#ifndef GT4_REBALANCE_ALL
+#define GT4_REBALANCE_ALL 0        // experiments: setmaxnreg also in the 256- and 512-consumer shapes with 4 stages (8 helper warps)
+#endif
+#ifndef GT4_INTERIOR_MERGE
+#define GT4_INTERIOR_MERGE 1      // full tiles away from the ends of the lists take the merge loop without cursor bounds
+#endif
+#ifndef GT4_CLAIM_MODE
+#define GT4_CLAIM_MODE 0          // when the producer claims a tile: 0 = one stage ahead, 1 = when the stage is free, 2 = when its previous tile has its offset
+#endif
+#ifndef GT4_HELPER_SLEEP_NS
+#define GT4_HELPER_SLEEP_NS 0      // > 0: the helper warps sleep between two looks at a barrier they wait for
+#endif
 constexpr int STORE_WARPS = GT4_STORE_WARPS;
+
+__device__ __forceinline__ void helper_wait (uint64_t *bar, uint32_t parity)
+{
+#if GT4_HELPER_SLEEP_NS > 0
+  dev::mbar_wait_sleep (bar, parity, GT4_HELPER_SLEEP_NS);
+#else
+  dev::mbar_wait_relaxed (bar, parity);
+#endif
+}
 constexpr uint64_t TILE_END = ~0ull;
 
 using namespace dev;
@@ -63,6 +84,10 @@ struct StreamCfg {
   static constexpr int GROUP = NC / GT4_SPLIT_POINTS;         // consumer threads per coarse co-rank (the splitter warp searches 32 co-ranks per round)
   static constexpr int NSPLIT = NC / GROUP + 1;
   static constexpr int MIN_CTAS = (NC <= 256) ? 2 : 1;
+  // 768 consumers + 8 helper warps = 1024 threads start with 64 registers each; the helper warpgroups then hand registers
+  // over to the consumer warpgroups (setmaxnreg)
+  static constexpr bool REBALANCE_REGS = (NC == 768) || (GT4_REBALANCE_ALL && S == 4);
+  static constexpr int CONSUMER_REGS = (NC == 768) ? 72 : (NC == 512) ? 96 : 88, HELPER_REGS = 40;
   static constexpr int TILE = CONSUMERS * VT;
   // A and B slices are over-fetched to 16-byte boundaries on both sides and carry +1 halo / +1 peek;
   // merge_slots may read VT + 1 elements past a slice
@@ -77,7 +102,7 @@ struct StageMeta {
   int na, nb;        // slice lengths
   int ka, kb;        // element offset of A[a_lo] / B[b_lo] inside the stage's key array
   int ca, cb;        // same inside the count array
-  int flags;         // bit 0: halo present (A[a_lo - 1]), bit 1: peek present (B[b_hi])
+  int flags;         // bit 0: halo present (A[a_lo - 1]), bit 1: peek present (B[b_hi]), bit 2: full tile with both and A[a_hi]
 };
 
 struct Mailbox {
@@ -168,6 +193,10 @@ setop2_stream_kernel (const TileArgs args)
   auto stage_keys = [&] (int s) { return reinterpret_cast<uint64_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES); };
   auto stage_cnts = [&] (int s) { return reinterpret_cast<uint32_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES + (size_t) Cfg::KSLOTS * 8); };
 
+  static_assert (!Cfg::REBALANCE_REGS || (NC % 128 == 0 && (Cfg::NTHREADS - NC) % 128 == 0), "setmaxnreg acts on warpgroups");
+  if (warp >= NWARPS) {       // ---- the helper warps (with REBALANCE_REGS: two whole warpgroups) ----
+  if (Cfg::REBALANCE_REGS) asm volatile ("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(Cfg::HELPER_REGS));
+
   // ============================================================================ producer
   if (warp == PRODUCER_WARP) {
     if (lane != 0) return;
@@ -194,7 +223,31 @@ setop2_stream_kernel (const TileArgs args)
     if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
     int s = 0;
     uint32_t ph = 0;
+    bool first = true;
     while (true) {
+#if GT4_CLAIM_MODE >= 1
+      // A ticket fixes the tile's place in the output order, and every later tile's look-back waits until this tile has
+      // been merged: claim as LATE as possible.  (Mode 0 claimed the following tile before waiting for a free stage; the
+      // wait varies between 0 and a tile period from CTA to CTA, and exactly that spread is what the look-backs of the
+      // other CTAs then wait for.)  Mode 2 claims when the stage's previous tile has got its output offset, i.e. while its
+      // store runs; mode 1 when the stage is free.
+      if (!first) {
+#if GT4_CLAIM_MODE == 2
+        if (!COUNT_ONLY) helper_wait (&bar_base[s], ph ^ 1u);
+        else helper_wait (&bar_empty[s], ph ^ 1u);
+#else
+        helper_wait (&bar_empty[s], ph ^ 1u);
+#endif
+        nxt = atomicAdd (&args.hdr->ticket, 1u);
+        if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
+        pf_tile = nxt + pf_dist;
+        if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
+      }
+      first = false;
+      const uint64_t tile = nxt, a_lo = nxt_lo, a_hi = nxt_hi;
+      const uint64_t cur_pf = pf_tile, cur_pf_lo = pf_lo, cur_pf_hi = pf_hi;
+#else
+      (void) first;
       const uint64_t tile = nxt, a_lo = nxt_lo, a_hi = nxt_hi;
       const uint64_t cur_pf = pf_tile, cur_pf_lo = pf_lo, cur_pf_hi = pf_hi;
       if (tile < n_tiles) {     // claim the following tile now: its latency hides behind the wait below
@@ -203,6 +256,7 @@ setop2_stream_kernel (const TileArgs args)
         pf_tile = nxt + pf_dist;
         if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
       }
+#endif
       if (!COUNT_ONLY && (args.debug & 4) == 0 && cur_pf < n_tiles && cur_pf_hi >= cur_pf_lo && cur_pf_hi - cur_pf_lo <= (uint64_t) TILE) {   // (the count-only pass is faster without it)
         const uint64_t pd_lo = cur_pf * TILE;
         const uint64_t pd_hi = (pd_lo + TILE < total) ? pd_lo + TILE : total;
@@ -212,7 +266,7 @@ setop2_stream_kernel (const TileArgs args)
         prefetch_l2 (args.a_counts + cur_pf_lo, (cur_pf_hi - cur_pf_lo) * 4);
         prefetch_l2 (args.b_counts + pb_lo, (pb_hi - pb_lo) * 4);
       }
-      mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
+      helper_wait (&bar_empty[s], ph ^ 1u);
 #if !GT4_STORE_FENCE
       fence_proxy_async ();      // the stage's last generic-proxy accesses (observed through bar_empty) before the TMA writes
 #endif
@@ -221,7 +275,7 @@ setop2_stream_kernel (const TileArgs args)
         // (each look-back warp owns one stage and must see its own marker; a barrier may never be advanced
         // twice before its waiter has looked)
         for (int q = 0; q < (COUNT_ONLY ? 1 : STAGES); q++) {
-          if (q > 0) mbar_wait_relaxed (&bar_empty[s], ph ^ 1u);
+          if (q > 0) helper_wait (&bar_empty[s], ph ^ 1u);
           s_meta[s].tile = TILE_END;
           mbar_arrive (&bar_full[s]);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -238,15 +292,16 @@ setop2_stream_kernel (const TileArgs args)
       const uint64_t b_lo = d_lo - a_lo, b_hi = sane ? d_hi - a_hi : b_lo;
       const int na = (int) (a_hi_ok - a_lo), nb = (int) (b_hi - b_lo);
       const int halo = a_lo > 0 ? 1 : 0, peek = b_hi < args.nb ? 1 : 0;
+      const int peek_a = (sane && a_hi < args.na) ? 1 : 0;       // the element of A after the tile: a natural sentinel (merge_slots_interior)
       uint64_t *sk = stage_keys (s);
       uint32_t *sc = stage_cnts (s);
 
       // Byte ranges to stage.  A block is laid out from the 16-byte boundary below its first byte to the one above
       // its last byte (TMA bulk copies need 16-byte aligned addresses and sizes).  Nothing outside the arrays is
       // ever read: see the edge case below.
-      const uintptr_t ak0 = (uintptr_t) (args.a_words + a_lo - halo), ak1 = (uintptr_t) (args.a_words + a_hi_ok);
+      const uintptr_t ak0 = (uintptr_t) (args.a_words + a_lo - halo), ak1 = (uintptr_t) (args.a_words + a_hi_ok + peek_a);
       const uintptr_t bk0 = (uintptr_t) (args.b_words + b_lo), bk1 = (uintptr_t) (args.b_words + b_hi + peek);
-      const uintptr_t ac0 = (uintptr_t) (args.a_counts + a_lo - halo), ac1 = (uintptr_t) (args.a_counts + a_hi_ok);
+      const uintptr_t ac0 = (uintptr_t) (args.a_counts + a_lo - halo), ac1 = (uintptr_t) (args.a_counts + a_hi_ok + peek_a);
       const uintptr_t bc0 = (uintptr_t) (args.b_counts + b_lo), bc1 = (uintptr_t) (args.b_counts + b_hi + peek);
       const uintptr_t ak0a = ak0 & ~(uintptr_t) 15, bk0a = bk0 & ~(uintptr_t) 15, ac0a = ac0 & ~(uintptr_t) 15, bc0a = bc0 & ~(uintptr_t) 15;
       const uint32_t ak_bytes = (ak1 > ak0) ? (uint32_t) (((ak1 + 15) & ~(uintptr_t) 15) - ak0a) : 0u;
@@ -262,7 +317,7 @@ setop2_stream_kernel (const TileArgs args)
       m.kb = (int) (ak_bytes >> 3) + (int) ((bk0 - bk0a) >> 3);      // B keys follow the A block
       m.ca = (int) ((ac0 - ac0a) >> 2) + halo;
       m.cb = (int) (ac_bytes >> 2) + (int) ((bc0 - bc0a) >> 2);
-      m.flags = halo | (peek << 1);
+      m.flags = halo | (peek << 1) | ((halo && peek && peek_a && d_hi - d_lo == (uint64_t) TILE) ? 4 : 0);   // bit 2: interior tile
       s_meta[s] = m;
 
       unsigned char *skb = reinterpret_cast<unsigned char *> (sk), *scb = reinterpret_cast<unsigned char *> (sc);
@@ -320,8 +375,12 @@ setop2_stream_kernel (const TileArgs args)
   if (warp == SPLITTER_WARP) {
     int s = 0, n_end = 0;
     uint32_t ph = 0;
+    const bool sprof = (args.debug & 32) != 0;
+    long long t_sfull = 0, t_ssearch = 0;
     while (true) {
+      const long long s0 = sprof ? clock64 () : 0;
       mbar_wait (&bar_full[s], ph);
+      const long long s1 = sprof ? clock64 () : 0;
       const StageMeta m = s_meta[s];
       if (m.tile != TILE_END) {
         const uint64_t *sk = stage_keys (s);
@@ -339,8 +398,13 @@ setop2_stream_kernel (const TileArgs args)
       }
       __syncwarp ();
       if (lane == 0) mbar_arrive (&bar_split[s]);
+      if (sprof) { t_sfull += s1 - s0; t_ssearch += clock64 () - s1; }
       if (m.tile == TILE_END && ++n_end == (COUNT_ONLY ? 1 : STAGES)) break;
       if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    if (sprof && lane == 0) {        // experiments: how long the splitter waits for the TMA, how long its searches take
+      atomicAdd (&args.hdr->dbg[2], (unsigned long long) t_sfull);
+      atomicAdd (&args.hdr->dbg[3], (unsigned long long) t_ssearch);
     }
     return;
   }
@@ -354,7 +418,7 @@ setop2_stream_kernel (const TileArgs args)
     uint32_t ph = 0;
     LookbackStats stats = {0, 0, 0, 0};
     for (uint32_t it = (uint32_t) s;; it += STAGES, ph ^= 1u) {
-      mbar_wait_relaxed (&bar_agg[s], ph);
+      helper_wait (&bar_agg[s], ph);
       if (it >= s_n_iter) break;                  // the END marker, not a tile
       const uint64_t tile = s_mail[s].tile;
       const uint64_t base = (args.debug & 1) ? tile * TILE
@@ -383,16 +447,18 @@ setop2_stream_kernel (const TileArgs args)
     int s = 0;
     uint32_t ph = 0;
     while (true) {
-      mbar_wait_relaxed (&bar_comp[s], ph);
+      helper_wait (&bar_comp[s], ph);
       if (s_mail[s].tile == TILE_END) break;      // every real tile precedes the first END marker
-      mbar_wait_relaxed (&bar_base[s], ph);
+      helper_wait (&bar_base[s], ph);
       const uint64_t base = s_mail[s].base;
       const int cnt = s_mail[s].cnt;
       const uint64_t *sk = stage_keys (s);
       const uint32_t *sc = stage_cnts (s);
       if (args.debug & 8) {
         // experiment: no stores
-      } else if (base + (uint64_t) cnt <= args.out_capacity[stream]) {
+      } else if (base + (uint64_t) cnt > args.out_capacity[stream]) {
+        if (st_tid == 0) args.hdr->overflow = 1u;
+      } else {
         uint64_t *ow = args.out_words[stream] + base;
         uint32_t *oc = args.out_counts[stream] + base;
         int x = st_tid;
@@ -413,8 +479,6 @@ setop2_stream_kernel (const TileArgs args)
           for (int r = 0; r < 8; r++) oc[x + r * ST_THREADS] = c[r];
         }
         for (; x < cnt; x += ST_THREADS) oc[x] = sc[x];
-      } else if (st_tid == 0) {
-        args.hdr->overflow = 1u;
       }
 #if GT4_STORE_FENCE
       fence_proxy_async ();          // generic accesses to the stage before the async proxy (TMA) refills it
@@ -425,8 +489,11 @@ setop2_stream_kernel (const TileArgs args)
     }
     return;
   }
+  return;
+  }       // ---- end of the helper warps ----
 
   // ============================================================================ consumers
+  if (Cfg::REBALANCE_REGS) asm volatile ("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(Cfg::CONSUMER_REGS));
   const int stream = args.stream0;
   unsigned long long acc_n = 0, acc_sum = 0;   // this thread's share of the header totals
   int s = 0, n_end = 0;
@@ -468,14 +535,18 @@ setop2_stream_kernel (const TileArgs args)
     uint64_t o_key[VT];
     uint32_t o_freq[VT];
     uint32_t mask = 0;
-    merge_slots<VT> (ka, ca, m.na, (m.flags & 1) != 0, kb, cb, m.nb, (m.flags & 2) != 0, i0, d0,
-      [&] (int sl, uint64_t key, uint32_t c1, uint32_t c2, bool in_a, bool in_b, bool live) {
+    auto sink = [&] (int sl, uint64_t key, uint32_t c1, uint32_t c2, bool in_a, bool in_b, bool live) {
         uint32_t f = 0;
         const bool keep = eval_fast<FAST> (args.p, stream, c1, c2, in_a, in_b, f) && live;
         o_key[sl] = key;
         o_freq[sl] = f;
         mask |= (keep ? 1u : 0u) << sl;
-      });
+      };
+#if GT4_INTERIOR_MERGE
+    if (m.flags & 4) merge_slots_interior<VT> (ka, ca, kb, cb, i0, d0, sink);
+    else
+#endif
+    merge_slots<VT> (ka, ca, m.na, (m.flags & 1) != 0, kb, cb, m.nb, (m.flags & 2) != 0, i0, d0, sink);
     const int cnt = __popc (mask);
     acc_n += (unsigned) cnt;
 #pragma unroll
@@ -599,7 +670,7 @@ cudaError_t launch_stream_fast (const TileArgs &args, int fast, int sm_count, cu
 }  // namespace
 
 // supported (consumer threads, items per thread, stages) triples; the stage count is fixed per shape by shared memory
-#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 4) X (256, 11, 3) X (384, 9, 5) X (384, 11, 4) X (512, 7, 5) X (512, 9, 4) X (512, 11, 3)
+#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 4) X (256, 11, 3) X (384, 9, 5) X (384, 11, 4) X (512, 7, 5) X (512, 9, 4) X (512, 11, 3) X (768, 5, 4) X (768, 6, 4)
 
 bool stream_shape_supported (int consumers, int items)
 {

@@ -26,7 +26,7 @@ static void run (const uint64_t *aw, const uint32_t *ac, uint64_t na, const uint
     if (diag > total) diag = total;
     part[t] = merge_path<uint64_t> (aw, na, bw, nb, diag);
   }
-  const int slots = (int) tile + VT + 4;
+  const int slots = (int) tile + VT + 5;
   std::vector<uint64_t> sk (slots);
   std::vector<uint32_t> sc (slots);
   for (uint64_t t = 0; t < n_tiles; t++) {
@@ -34,18 +34,20 @@ static void run (const uint64_t *aw, const uint32_t *ac, uint64_t na, const uint
     const uint64_t a_lo = part[t], a_hi = part[t + 1];
     const uint64_t b_lo = d_lo - a_lo, b_hi = d_hi - a_hi;
     const int tna = (int) (a_hi - a_lo), tnb = (int) (b_hi - b_lo);
-    const bool has_halo = a_lo > 0, has_peek = b_hi < nb;
+    const bool has_halo = a_lo > 0, has_peek = b_hi < nb, has_peek_a = a_hi < na;
     // poison the slack so that any use of it shows up
     for (int x = 0; x < slots; x++) { sk[x] = 0xDEADBEEFDEADBEEFull ^ (uint64_t) x; sc[x] = 0xABCD0000u + x; }
-    for (int x = 0; x < tna + tnb + 2; x++) {
+    // layout: [halo of A][A slice][element of A after the tile][B slice][peek of B]
+    for (int x = 0; x < tna + tnb + 3; x++) {
       uint64_t k = 0; uint32_t c = 0;
-      if (x <= tna) { if (x > 0 || has_halo) { k = aw[a_lo + x - 1]; c = ac[a_lo + x - 1]; } }
-      else { int j = x - 1 - tna; if (j < tnb || has_peek) { k = bw[b_lo + j]; c = bc[b_lo + j]; } }
+      if (x <= tna + 1) { if ((x > 0 || has_halo) && (x <= tna || has_peek_a)) { k = aw[a_lo + x - 1]; c = ac[a_lo + x - 1]; } }
+      else { int j = x - 2 - tna; if (j < tnb || has_peek) { k = bw[b_lo + j]; c = bc[b_lo + j]; } }
       sk[x] = k; sc[x] = c;
     }
     const uint64_t *ka = sk.data () + 1; const uint32_t *ca = sc.data () + 1;
-    const uint64_t *kb = ka + tna; const uint32_t *cb = ca + tna;
+    const uint64_t *kb = ka + tna + 1; const uint32_t *cb = ca + tna + 1;
     const int n_tile = tna + tnb;
+    const bool interior = has_halo && has_peek && has_peek_a && (uint64_t) n_tile == tile;   // what the stream kernel's producer flags
     // coarse co-ranks every 8 threads (what the splitter warp of setop2_stream_kernel computes)
     const int n_split = (nt + 7) / 8 + 1;
     std::vector<int> split (n_split);
@@ -57,8 +59,7 @@ static void run (const uint64_t *aw, const uint32_t *ac, uint64_t na, const uint
       const int d0 = (tid * VT < n_tile) ? tid * VT : n_tile;
       const int i0 = merge_path_window<int> (ka, tna, kb, tnb, d0, split[tid / 8], split[tid / 8 + 1]);
       if (i0 != merge_path<int> (ka, tna, kb, tnb, d0)) __builtin_trap ();
-      merge_slots<VT> (ka, ca, tna, has_halo, kb, cb, tnb, has_peek, i0, d0,
-        [&] (int, uint64_t key, uint32_t c1, uint32_t c2, bool in_a, bool in_b, bool live) {
+      auto sink = [&] (int, uint64_t key, uint32_t c1, uint32_t c2, bool in_a, bool in_b, bool live) {
           for (int q = 0; q < 4; q++) {
             if (!((mask >> q) & 1u)) continue;
             uint32_t f = 0;
@@ -68,7 +69,9 @@ static void run (const uint64_t *aw, const uint32_t *ac, uint64_t na, const uint
               sum_out[q] += f;
             }
           }
-        });
+        };
+      if (interior) merge_slots_interior<VT> (ka, ca, kb, cb, i0, d0, sink);
+      else merge_slots<VT> (ka, ca, tna, has_halo, kb, cb, tnb, has_peek, i0, d0, sink);
     }
   }
 }
