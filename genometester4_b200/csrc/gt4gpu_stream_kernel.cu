@@ -42,11 +42,12 @@ namespace {
 #ifndef GT4_STORE_WARPS
 #define GT4_STORE_WARPS 2
 #endif
-#ifndef GT4_REBALANCE_ALL
-#define GT4_REBALANCE_ALL 0        // experiments: setmaxnreg also in the 256- and 512-consumer shapes with 4 stages (8 helper warps)
-#endif
+constexpr int STORE_WARPS = GT4_STORE_WARPS;
 #ifndef GT4_INTERIOR_MERGE
 #define GT4_INTERIOR_MERGE 1      // full tiles away from the ends of the lists take the merge loop without cursor bounds
+#endif
+#ifndef GT4_DENSE_STORE
+#define GT4_DENSE_STORE 0          // (measured slower, 11.7 vs 10.4 ms: kept for experiments) tiles keeping at least half of their slots leave the compaction to the store warps
 #endif
 #ifndef GT4_CLAIM_MODE
 #define GT4_CLAIM_MODE 0          // when the producer claims a tile: 0 = one stage ahead, 1 = when the stage is free, 2 = when its previous tile has its offset
@@ -54,8 +55,6 @@ namespace {
 #ifndef GT4_HELPER_SLEEP_NS
 #define GT4_HELPER_SLEEP_NS 0      // > 0: the helper warps sleep between two looks at a barrier they wait for
 #endif
-constexpr int STORE_WARPS = GT4_STORE_WARPS;
-
 __device__ __forceinline__ void helper_wait (uint64_t *bar, uint32_t parity)
 {
 #if GT4_HELPER_SLEEP_NS > 0
@@ -84,10 +83,6 @@ struct StreamCfg {
   static constexpr int GROUP = NC / GT4_SPLIT_POINTS;         // consumer threads per coarse co-rank (the splitter warp searches 32 co-ranks per round)
   static constexpr int NSPLIT = NC / GROUP + 1;
   static constexpr int MIN_CTAS = (NC <= 256) ? 2 : 1;
-  // 768 consumers + 8 helper warps = 1024 threads start with 64 registers each; the helper warpgroups then hand registers
-  // over to the consumer warpgroups (setmaxnreg)
-  static constexpr bool REBALANCE_REGS = (NC == 768) || (GT4_REBALANCE_ALL && S == 4);
-  static constexpr int CONSUMER_REGS = (NC == 768) ? 72 : (NC == 512) ? 96 : 88, HELPER_REGS = 40;
   static constexpr int TILE = CONSUMERS * VT;
   // A and B slices are over-fetched to 16-byte boundaries on both sides and carry +1 halo / +1 peek;
   // merge_slots may read VT + 1 elements past a slice
@@ -109,6 +104,8 @@ struct Mailbox {
   uint64_t tile;
   uint64_t base;     // exclusive prefix of the tile's output count (written by the look-back warp)
   int cnt;           // the tile's output count (written by consumer thread 0)
+  int dense;         // 1: the stage holds ALL merged slots in place plus a keep mask per thread, the store warps compact
+  int part[STORE_WARPS];   // dense tiles: survivors before store warp w's share of the slots
 };
 
 // All 32 lanes of the look-back warp; returns the exclusive prefix of `aggregate`.
@@ -168,6 +165,7 @@ setop2_stream_kernel (const TileArgs args)
   __shared__ Mailbox s_mail[STAGES];
   __shared__ int s_split[STAGES][NSPLIT];
   __shared__ int s_wcnt[2][NWARPS];
+  __shared__ uint16_t s_mask[GT4_DENSE_STORE ? STAGES : 1][GT4_DENSE_STORE ? NC : 1];   // dense tiles: which of a thread's VT slots survive
   __shared__ volatile unsigned int s_n_iter;            // tiles this CTA ended up processing (set when the END marker arrives)
   __shared__ unsigned long long s_red[2][NWARPS];
 
@@ -192,10 +190,6 @@ setop2_stream_kernel (const TileArgs args)
 
   auto stage_keys = [&] (int s) { return reinterpret_cast<uint64_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES); };
   auto stage_cnts = [&] (int s) { return reinterpret_cast<uint32_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES + (size_t) Cfg::KSLOTS * 8); };
-
-  static_assert (!Cfg::REBALANCE_REGS || (NC % 128 == 0 && (Cfg::NTHREADS - NC) % 128 == 0), "setmaxnreg acts on warpgroups");
-  if (warp >= NWARPS) {       // ---- the helper warps (with REBALANCE_REGS: two whole warpgroups) ----
-  if (Cfg::REBALANCE_REGS) asm volatile ("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(Cfg::HELPER_REGS));
 
   // ============================================================================ producer
   if (warp == PRODUCER_WARP) {
@@ -458,6 +452,48 @@ setop2_stream_kernel (const TileArgs args)
         // experiment: no stores
       } else if (base + (uint64_t) cnt > args.out_capacity[stream]) {
         if (st_tid == 0) args.hdr->overflow = 1u;
+#if GT4_DENSE_STORE
+      } else if (s_mail[s].dense) {
+        // The stage holds every merged slot at its own place (thread t, slot j -> t * VT + j).  Each store warp walks its
+        // share of the slots in rows of 32 (conflict-free loads), ranks the survivors of a row with a ballot and writes
+        // them to consecutive addresses.
+        static_assert (TILE % (32 * STORE_WARPS) == 0, "whole rows per store warp");
+        constexpr int ROWS = TILE / (32 * STORE_WARPS), BATCH = 8;
+        const int my = warp - STORE_WARP0;
+        uint64_t *ow = args.out_words[stream] + base + (uint64_t) s_mail[s].part[my];
+        uint32_t *oc = args.out_counts[stream] + base + (uint64_t) s_mail[s].part[my];
+        const uint32_t lt = (1u << lane) - 1u;
+        int m0 = my * (ROWS * 32) + lane;
+        for (int r0 = 0; r0 < ROWS; r0 += BATCH) {
+          uint64_t k[BATCH];
+          uint32_t c[BATCH], mk[BATCH];
+#pragma unroll
+          for (int r = 0; r < BATCH; r++) {
+            const int m = m0 + 32 * r;
+            if (r0 + r < ROWS) {
+              const int t = m / VT;
+              k[r] = sk[m];
+              c[r] = sc[m];
+              mk[r] = ((uint32_t) s_mask[s][t] >> (m - t * VT)) & 1u;
+            } else {
+              k[r] = 0; c[r] = 0; mk[r] = 0;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < BATCH; r++) {
+            const uint32_t ball = __ballot_sync (0xffffffffu, mk[r] != 0u);
+            if (mk[r]) {
+              const int at = __popc (ball & lt);
+              ow[at] = k[r];
+              oc[at] = c[r];
+            }
+            const int adv = __popc (ball);
+            ow += adv;
+            oc += adv;
+          }
+          m0 += 32 * BATCH;
+        }
+#endif
       } else {
         uint64_t *ow = args.out_words[stream] + base;
         uint32_t *oc = args.out_counts[stream] + base;
@@ -489,11 +525,8 @@ setop2_stream_kernel (const TileArgs args)
     }
     return;
   }
-  return;
-  }       // ---- end of the helper warps ----
 
   // ============================================================================ consumers
-  if (Cfg::REBALANCE_REGS) asm volatile ("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(Cfg::CONSUMER_REGS));
   const int stream = args.stream0;
   unsigned long long acc_n = 0, acc_sum = 0;   // this thread's share of the header totals
   int s = 0, n_end = 0;
@@ -582,12 +615,29 @@ setop2_stream_kernel (const TileArgs args)
     }
     const int tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
     const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
+    const bool dense = GT4_DENSE_STORE && 2 * tile_cnt >= TILE;
     if (tid == 0) {
       s_mail[s].tile = m.tile;
       s_mail[s].cnt = tile_cnt;
+      s_mail[s].dense = dense ? 1 : 0;
       mbar_arrive (&bar_agg[s]);    // the look-back warp takes it from here
     }
 
+    if (dense) {
+      // most slots survive: every slot goes to its own place in the stage (stride VT between lanes, VT odd: no bank
+      // conflicts) with a keep mask per thread, and the store warps drop the dead slots on their way out.  Scattering
+      // the survivors to their compacted positions costs 2-3 times the shared-memory wavefronts (random conflicts).
+#pragma unroll
+      for (int sl = 0; sl < VT; sl++) {
+        sk[tid * VT + sl] = o_key[sl];
+        sc[tid * VT + sl] = o_freq[sl];
+      }
+#if GT4_DENSE_STORE
+      s_mask[s][tid] = (uint16_t) mask;
+      static_assert (NWARPS % STORE_WARPS == 0, "store warps split the consumer warps evenly");
+      if (lane == 0 && warp % (NWARPS / STORE_WARPS) == 0) s_mail[s].part[warp / (NWARPS / STORE_WARPS)] = warp_prefix;
+#endif
+    } else {
     // compact this tile's survivors to the front of its own stage buffer, then hand it to the store warps
     int pos = warp_prefix + incl - cnt;
 #pragma unroll
@@ -597,6 +647,7 @@ setop2_stream_kernel (const TileArgs args)
         sc[pos] = o_freq[sl];
         pos += 1;
       }
+    }
     }
     __syncwarp ();
     if (lane == 0) mbar_arrive (&bar_comp[s]);
@@ -670,7 +721,7 @@ cudaError_t launch_stream_fast (const TileArgs &args, int fast, int sm_count, cu
 }  // namespace
 
 // supported (consumer threads, items per thread, stages) triples; the stage count is fixed per shape by shared memory
-#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 4) X (256, 11, 3) X (384, 9, 5) X (384, 11, 4) X (512, 7, 5) X (512, 9, 4) X (512, 11, 3) X (768, 5, 4) X (768, 6, 4)
+#define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 4) X (256, 11, 3) X (384, 9, 5) X (384, 11, 4) X (512, 7, 5) X (512, 9, 4) X (512, 11, 3)
 
 bool stream_shape_supported (int consumers, int items)
 {
