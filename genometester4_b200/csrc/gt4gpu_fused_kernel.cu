@@ -321,15 +321,16 @@ setop2_fused_kernel (const TileArgs args)
       const uint64_t b_lo = d_lo - a_lo, b_hi = sane ? d_hi - a_hi : b_lo;
       const int na = (int) (a_hi_ok - a_lo), nb = (int) (b_hi - b_lo);
       const int halo = a_lo > 0 ? 1 : 0, peek = b_hi < args.nb ? 1 : 0;
+      const int peek_a = (sane && a_hi < args.na) ? 1 : 0;       // the element of A after the tile: a natural sentinel (merge_slots_interior)
       uint64_t *sk = stage_keys (s);
       uint32_t *sc = stage_cnts (s);
 
       // Byte ranges to stage.  A block is laid out from the 16-byte boundary below its first byte to the one above
       // its last byte (TMA bulk copies need 16-byte aligned addresses and sizes).  Nothing outside the arrays is
       // ever read: see the edge case below.
-      const uintptr_t ak0 = (uintptr_t) (args.a_words + a_lo - halo), ak1 = (uintptr_t) (args.a_words + a_hi_ok);
+      const uintptr_t ak0 = (uintptr_t) (args.a_words + a_lo - halo), ak1 = (uintptr_t) (args.a_words + a_hi_ok + peek_a);
       const uintptr_t bk0 = (uintptr_t) (args.b_words + b_lo), bk1 = (uintptr_t) (args.b_words + b_hi + peek);
-      const uintptr_t ac0 = (uintptr_t) (args.a_counts + a_lo - halo), ac1 = (uintptr_t) (args.a_counts + a_hi_ok);
+      const uintptr_t ac0 = (uintptr_t) (args.a_counts + a_lo - halo), ac1 = (uintptr_t) (args.a_counts + a_hi_ok + peek_a);
       const uintptr_t bc0 = (uintptr_t) (args.b_counts + b_lo), bc1 = (uintptr_t) (args.b_counts + b_hi + peek);
       const uintptr_t ak0a = ak0 & ~(uintptr_t) 15, bk0a = bk0 & ~(uintptr_t) 15, ac0a = ac0 & ~(uintptr_t) 15, bc0a = bc0 & ~(uintptr_t) 15;
       const uint32_t ak_bytes = (ak1 > ak0) ? (uint32_t) (((ak1 + 15) & ~(uintptr_t) 15) - ak0a) : 0u;
@@ -345,7 +346,7 @@ setop2_fused_kernel (const TileArgs args)
       m.kb = (int) (ak_bytes >> 3) + (int) ((bk0 - bk0a) >> 3);      // B keys follow the A block
       m.ca = (int) ((ac0 - ac0a) >> 2) + halo;
       m.cb = (int) (ac_bytes >> 2) + (int) ((bc0 - bc0a) >> 2);
-      m.flags = halo | (peek << 1);
+      m.flags = halo | (peek << 1) | ((halo && peek && peek_a && d_hi - d_lo == (uint64_t) TILE) ? 4 : 0);   // bit 2: interior tile
       s_meta[s] = m;
 
       unsigned char *skb = reinterpret_cast<unsigned char *> (sk), *scb = reinterpret_cast<unsigned char *> (sc);
@@ -540,8 +541,7 @@ setop2_fused_kernel (const TileArgs args)
     uint64_t o_key[VT];
     uint32_t o_fu[VT], o_fx[VT];
     uint32_t mask_u = 0, kinds = 0;              // kinds: 2 bits per slot, 0 = no rest output, 1..3 = intersection / diff1 / diff2
-    merge_slots<VT> (ka, ca, m.na, (m.flags & 1) != 0, kb, cb, m.nb, (m.flags & 2) != 0, i0, d0,
-      [&] (int sl, uint64_t key, uint32_t c1, uint32_t c2, bool in_a, bool in_b, bool live) {
+    auto sink = [&] (int sl, uint64_t key, uint32_t c1, uint32_t c2, bool in_a, bool in_b, bool live) {
         uint32_t f = 0, fx = 0, kind = 0;
         bool keep_u = false;
         if (DEFAULT_RULES) {
@@ -571,7 +571,9 @@ setop2_fused_kernel (const TileArgs args)
         o_fx[sl] = fx;
         mask_u |= (keep_u ? 1u : 0u) << sl;
         kinds |= kind << (2 * sl);
-      });
+      };
+    if (m.flags & 4) merge_slots_interior<VT> (ka, ca, kb, cb, i0, d0, sink);     // full tile away from the ends of the lists: no cursor bounds
+    else merge_slots<VT> (ka, ca, m.na, (m.flags & 1) != 0, kb, cb, m.nb, (m.flags & 2) != 0, i0, d0, sink);
     int cnt[4] = {__popc (mask_u), 0, 0, 0};
 #pragma unroll
     for (int sl = 0; sl < VT; sl++) {

@@ -165,7 +165,6 @@ setop2_stream_kernel (const TileArgs args)
   __shared__ Mailbox s_mail[STAGES];
   __shared__ int s_split[STAGES][NSPLIT];
   __shared__ int s_wcnt[2][NWARPS];
-  __shared__ uint16_t s_mask[GT4_DENSE_STORE ? STAGES : 1][GT4_DENSE_STORE ? NC : 1];   // dense tiles: which of a thread's VT slots survive
   __shared__ volatile unsigned int s_n_iter;            // tiles this CTA ended up processing (set when the END marker arrives)
   __shared__ unsigned long long s_red[2][NWARPS];
 
@@ -454,7 +453,8 @@ setop2_stream_kernel (const TileArgs args)
         if (st_tid == 0) args.hdr->overflow = 1u;
 #if GT4_DENSE_STORE
       } else if (s_mail[s].dense) {
-        // The stage holds every merged slot at its own place (thread t, slot j -> t * VT + j).  Each store warp walks its
+        // The stage holds every merged slot at its own place (thread t, slot j -> t * VT + j); a dead slot carries the
+        // count 0, which no record of a two-list merge can have (include_in_* demand freq != 0).  Each store warp walks its
         // share of the slots in rows of 32 (conflict-free loads), ranks the survivors of a row with a ballot and writes
         // them to consecutive addresses.
         static_assert (TILE % (32 * STORE_WARPS) == 0, "whole rows per store warp");
@@ -463,35 +463,28 @@ setop2_stream_kernel (const TileArgs args)
         uint64_t *ow = args.out_words[stream] + base + (uint64_t) s_mail[s].part[my];
         uint32_t *oc = args.out_counts[stream] + base + (uint64_t) s_mail[s].part[my];
         const uint32_t lt = (1u << lane) - 1u;
-        int m0 = my * (ROWS * 32) + lane;
+        const uint64_t *rk = sk + my * (ROWS * 32) + lane;
+        const uint32_t *rc = sc + my * (ROWS * 32) + lane;
+        int run = 0;
         for (int r0 = 0; r0 < ROWS; r0 += BATCH) {
           uint64_t k[BATCH];
-          uint32_t c[BATCH], mk[BATCH];
+          uint32_t c[BATCH];
 #pragma unroll
           for (int r = 0; r < BATCH; r++) {
-            const int m = m0 + 32 * r;
-            if (r0 + r < ROWS) {
-              const int t = m / VT;
-              k[r] = sk[m];
-              c[r] = sc[m];
-              mk[r] = ((uint32_t) s_mask[s][t] >> (m - t * VT)) & 1u;
-            } else {
-              k[r] = 0; c[r] = 0; mk[r] = 0;
-            }
+            const bool in = (ROWS % BATCH == 0) || r0 + r < ROWS;
+            k[r] = in ? rk[32 * (r0 + r)] : 0ull;
+            c[r] = in ? rc[32 * (r0 + r)] : 0u;
           }
 #pragma unroll
           for (int r = 0; r < BATCH; r++) {
-            const uint32_t ball = __ballot_sync (0xffffffffu, mk[r] != 0u);
-            if (mk[r]) {
-              const int at = __popc (ball & lt);
+            const uint32_t ball = __ballot_sync (0xffffffffu, c[r] != 0u);
+            if (c[r]) {
+              const int at = run + __popc (ball & lt);
               ow[at] = k[r];
               oc[at] = c[r];
             }
-            const int adv = __popc (ball);
-            ow += adv;
-            oc += adv;
+            run += __popc (ball);
           }
-          m0 += 32 * BATCH;
         }
 #endif
       } else {
@@ -615,7 +608,7 @@ setop2_stream_kernel (const TileArgs args)
     }
     const int tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
     const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
-    const bool dense = GT4_DENSE_STORE && 2 * tile_cnt >= TILE;
+    const bool dense = GT4_DENSE_STORE && args.p.sem == SEM_PAIR && !args.p.subtract && 2 * tile_cnt >= TILE;      // (N-list nodes and -du may keep a count of 0)
     if (tid == 0) {
       s_mail[s].tile = m.tile;
       s_mail[s].cnt = tile_cnt;
@@ -625,15 +618,14 @@ setop2_stream_kernel (const TileArgs args)
 
     if (dense) {
       // most slots survive: every slot goes to its own place in the stage (stride VT between lanes, VT odd: no bank
-      // conflicts) with a keep mask per thread, and the store warps drop the dead slots on their way out.  Scattering
+      // conflicts), and the store warps drop the dead slots on their way out.  Scattering
       // the survivors to their compacted positions costs 2-3 times the shared-memory wavefronts (random conflicts).
 #pragma unroll
       for (int sl = 0; sl < VT; sl++) {
         sk[tid * VT + sl] = o_key[sl];
-        sc[tid * VT + sl] = o_freq[sl];
+        sc[tid * VT + sl] = ((mask >> sl) & 1u) ? o_freq[sl] : 0u;       // 0 marks a dead slot
       }
 #if GT4_DENSE_STORE
-      s_mask[s][tid] = (uint16_t) mask;
       static_assert (NWARPS % STORE_WARPS == 0, "store warps split the consumer warps evenly");
       if (lane == 0 && warp % (NWARPS / STORE_WARPS) == 0) s_mail[s].part[warp / (NWARPS / STORE_WARPS)] = warp_prefix;
 #endif
