@@ -46,8 +46,8 @@ constexpr int STORE_WARPS = GT4_STORE_WARPS;
 #ifndef GT4_INTERIOR_MERGE
 #define GT4_INTERIOR_MERGE 1      // full tiles away from the ends of the lists take the merge loop without cursor bounds
 #endif
-#ifndef GT4_DENSE_STORE
-#define GT4_DENSE_STORE 0          // (measured slower, 11.7 vs 10.4 ms: kept for experiments) tiles keeping at least half of their slots leave the compaction to the store warps
+#ifndef GT4_STATIC_TILES
+#define GT4_STATIC_TILES 0
 #endif
 #ifndef GT4_CLAIM_MODE
 #define GT4_CLAIM_MODE 0          // when the producer claims a tile: 0 = one stage ahead, 1 = when the stage is free, 2 = when its previous tile has its offset
@@ -104,8 +104,6 @@ struct Mailbox {
   uint64_t tile;
   uint64_t base;     // exclusive prefix of the tile's output count (written by the look-back warp)
   int cnt;           // the tile's output count (written by consumer thread 0)
-  int dense;         // 1: the stage holds ALL merged slots in place plus a keep mask per thread, the store warps compact
-  int part[STORE_WARPS];   // dense tiles: survivors before store warp w's share of the slots
 };
 
 // All 32 lanes of the look-back warp; returns the exclusive prefix of `aggregate`.
@@ -207,7 +205,14 @@ setop2_stream_kernel (const TileArgs args)
         lim[2 * q + 1] = hi[q] & ~(uintptr_t) 15;
       }
     }
-    uint64_t nxt = atomicAdd (&args.hdr->ticket, 1u);
+#if GT4_STATIC_TILES
+    // experiment: tile = round * grid + CTA (needs every CTA of the grid resident; fewer look-back polls, no balancing)
+    uint64_t static_round = 0;
+#define GT4_CLAIM_TICKET() ((uint64_t) blockIdx.x + (static_round++) * (uint64_t) gridDim.x)
+#else
+#define GT4_CLAIM_TICKET() ((uint64_t) atomicAdd (&args.hdr->ticket, 1u))
+#endif
+    uint64_t nxt = GT4_CLAIM_TICKET ();
     uint64_t nxt_lo = 0, nxt_hi = 0;
     if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
     // L2 prefetch of the tiles the grid will claim about two rounds from now (co-ranks loaded one iteration early)
@@ -231,7 +236,7 @@ setop2_stream_kernel (const TileArgs args)
 #else
         helper_wait (&bar_empty[s], ph ^ 1u);
 #endif
-        nxt = atomicAdd (&args.hdr->ticket, 1u);
+        nxt = GT4_CLAIM_TICKET ();
         if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
         pf_tile = nxt + pf_dist;
         if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
@@ -244,7 +249,7 @@ setop2_stream_kernel (const TileArgs args)
       const uint64_t tile = nxt, a_lo = nxt_lo, a_hi = nxt_hi;
       const uint64_t cur_pf = pf_tile, cur_pf_lo = pf_lo, cur_pf_hi = pf_hi;
       if (tile < n_tiles) {     // claim the following tile now: its latency hides behind the wait below
-        nxt = atomicAdd (&args.hdr->ticket, 1u);
+        nxt = GT4_CLAIM_TICKET ();
         if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
         pf_tile = nxt + pf_dist;
         if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
@@ -451,42 +456,6 @@ setop2_stream_kernel (const TileArgs args)
         // experiment: no stores
       } else if (base + (uint64_t) cnt > args.out_capacity[stream]) {
         if (st_tid == 0) args.hdr->overflow = 1u;
-#if GT4_DENSE_STORE
-      } else if (s_mail[s].dense) {
-        // The stage holds every merged slot at its own place (thread t, slot j -> t * VT + j); a dead slot carries the
-        // count 0, which no record of a two-list merge can have (include_in_* demand freq != 0).  Each store warp walks its
-        // share of the slots in rows of 32 (conflict-free loads), ranks the survivors of a row with a ballot and writes
-        // them to consecutive addresses.
-        static_assert (TILE % (32 * STORE_WARPS) == 0, "whole rows per store warp");
-        constexpr int ROWS = TILE / (32 * STORE_WARPS), BATCH = 8;
-        const int my = warp - STORE_WARP0;
-        uint64_t *ow = args.out_words[stream] + base + (uint64_t) s_mail[s].part[my];
-        uint32_t *oc = args.out_counts[stream] + base + (uint64_t) s_mail[s].part[my];
-        const uint32_t lt = (1u << lane) - 1u;
-        const uint64_t *rk = sk + my * (ROWS * 32) + lane;
-        const uint32_t *rc = sc + my * (ROWS * 32) + lane;
-        int run = 0;
-        for (int r0 = 0; r0 < ROWS; r0 += BATCH) {
-          uint64_t k[BATCH];
-          uint32_t c[BATCH];
-#pragma unroll
-          for (int r = 0; r < BATCH; r++) {
-            const bool in = (ROWS % BATCH == 0) || r0 + r < ROWS;
-            k[r] = in ? rk[32 * (r0 + r)] : 0ull;
-            c[r] = in ? rc[32 * (r0 + r)] : 0u;
-          }
-#pragma unroll
-          for (int r = 0; r < BATCH; r++) {
-            const uint32_t ball = __ballot_sync (0xffffffffu, c[r] != 0u);
-            if (c[r]) {
-              const int at = run + __popc (ball & lt);
-              ow[at] = k[r];
-              oc[at] = c[r];
-            }
-            run += __popc (ball);
-          }
-        }
-#endif
       } else {
         uint64_t *ow = args.out_words[stream] + base;
         uint32_t *oc = args.out_counts[stream] + base;
@@ -608,28 +577,12 @@ setop2_stream_kernel (const TileArgs args)
     }
     const int tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
     const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
-    const bool dense = GT4_DENSE_STORE && args.p.sem == SEM_PAIR && !args.p.subtract && 2 * tile_cnt >= TILE;      // (N-list nodes and -du may keep a count of 0)
     if (tid == 0) {
       s_mail[s].tile = m.tile;
       s_mail[s].cnt = tile_cnt;
-      s_mail[s].dense = dense ? 1 : 0;
       mbar_arrive (&bar_agg[s]);    // the look-back warp takes it from here
     }
 
-    if (dense) {
-      // most slots survive: every slot goes to its own place in the stage (stride VT between lanes, VT odd: no bank
-      // conflicts), and the store warps drop the dead slots on their way out.  Scattering
-      // the survivors to their compacted positions costs 2-3 times the shared-memory wavefronts (random conflicts).
-#pragma unroll
-      for (int sl = 0; sl < VT; sl++) {
-        sk[tid * VT + sl] = o_key[sl];
-        sc[tid * VT + sl] = ((mask >> sl) & 1u) ? o_freq[sl] : 0u;       // 0 marks a dead slot
-      }
-#if GT4_DENSE_STORE
-      static_assert (NWARPS % STORE_WARPS == 0, "store warps split the consumer warps evenly");
-      if (lane == 0 && warp % (NWARPS / STORE_WARPS) == 0) s_mail[s].part[warp / (NWARPS / STORE_WARPS)] = warp_prefix;
-#endif
-    } else {
     // compact this tile's survivors to the front of its own stage buffer, then hand it to the store warps
     int pos = warp_prefix + incl - cnt;
 #pragma unroll
@@ -639,7 +592,6 @@ setop2_stream_kernel (const TileArgs args)
         sc[pos] = o_freq[sl];
         pos += 1;
       }
-    }
     }
     __syncwarp ();
     if (lane == 0) mbar_arrive (&bar_comp[s]);
