@@ -76,7 +76,10 @@ cudaError_t launch_setop2_fused (const TileArgs &args, int sm_count, cudaStream_
 
 // ---- single-pass N-list union / intersection (gt4gpu_kway_kernel.cu)
 static constexpr int KWAY_MAX_LISTS = 8;        // lists per pass (their heads live in registers); more lists go through several passes
-static constexpr int KWAY_SAMPLE = 128;         // every KWAY_SAMPLE-th word of every list is a boundary candidate
+#ifndef GT4_KWAY_SAMPLE
+#define GT4_KWAY_SAMPLE 128
+#endif
+static constexpr int KWAY_SAMPLE = GT4_KWAY_SAMPLE;         // every KWAY_SAMPLE-th word of every list is a boundary candidate
 #ifndef GT4_KWAY_CAP
 #define GT4_KWAY_CAP 4096
 #endif

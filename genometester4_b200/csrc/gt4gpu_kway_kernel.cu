@@ -35,6 +35,10 @@
 #include "gt4gpu_device.cuh"
 #include "gt4gpu_internal.h"
 
+#ifndef GT4_KWAY_CTAS
+#define GT4_KWAY_CTAS 1            // CTAs per SM (2 needs GT4_KWAY_CAP <= 2048)
+#endif
+
 namespace gt4gpu {
 
 namespace {
@@ -111,7 +115,7 @@ __device__ __forceinline__ uint32_t kw_fold (uint32_t f, uint32_t c, bool first,
 }
 
 template <int NL, int NC, int S, int MODE, bool COUNT_ONLY>
-__global__ void __launch_bounds__ (KwayCfg<NL, NC, S>::NTHREADS, 1)
+__global__ void __launch_bounds__ (KwayCfg<NL, NC, S>::NTHREADS, GT4_KWAY_CTAS)
 kway_tile_kernel (const KwayArgs args)
 {
   using Cfg = KwayCfg<NL, NC, S>;
@@ -652,7 +656,7 @@ cudaError_t launch_kway_one (const KwayArgs &args, int sm_count, cudaStream_t st
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  uint64_t grid = (uint64_t) sm_count;
+  uint64_t grid = (uint64_t) sm_count * GT4_KWAY_CTAS;
   if (grid > args.n_tiles) grid = args.n_tiles;
   kernel<<<(unsigned) grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>> (args);
   return cudaGetLastError ();
