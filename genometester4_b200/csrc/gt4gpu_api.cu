@@ -14,9 +14,12 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -598,8 +601,55 @@ static int write_span (int fd, const unsigned char *p, size_t bytes, int64_t off
   return 0;
 }
 
-// offset < 0: sequential write at the descriptor's position.  Large spans to a seekable file are cut into pieces written
-// with pwrite from a few threads (one thread copies into the page cache at 3-4 GB/s only).
+// A large span of a regular file, written through a shared mapping.  write / pwrite hold the inode's lock for the whole
+// call, so any number of threads writing ONE file share a single core's page-cache speed (3.6 GB/s measured on the GPU
+// boxes' tmpfs: 18 GB of union records took 5 s of a 5.4 s gt4gpu-compare pipeline).  Page faults on a shared mapping take
+// no inode lock, so the copy scales with the threads (6.8 GB/s with 8; reserving the blocks with fallocate first was slower,
+// 4.7 GB/s: profiles/r02_cli_file_pipeline.txt).  A page fault that cannot get a block raises SIGBUS instead of returning
+// ENOSPC, so the mapping is only used when the file system reports at least twice the span free; otherwise, and on any
+// failure, the caller falls back to pwrite.  The file is extended with a one-byte fallocate at the end of the span, which
+// never shrinks it (several processes write disjoint ranges of one file in the sharded path).
+// GT4GPU_NO_MAPPED_WRITES=1 disables the path.
+static bool write_mapped (int fd, const unsigned char *p, size_t bytes, int64_t at)
+{
+  static const bool disabled = getenv ("GT4GPU_NO_MAPPED_WRITES") != nullptr;
+  if (disabled) return false;
+  struct stat sb;
+  if (fstat (fd, &sb) != 0 || !S_ISREG (sb.st_mode)) return false;
+  struct statvfs vfs;
+  if (fstatvfs (fd, &vfs) != 0 || (double) vfs.f_bavail * (double) vfs.f_frsize < 2.0 * (double) bytes) return false;
+  char path[64];
+  snprintf (path, sizeof (path), "/proc/self/fd/%d", fd);
+  const int rw = open (path, O_RDWR);            // the caller's descriptor is usually write-only: a mapping needs read access
+  if (rw < 0) return false;
+  int r;
+  do r = fallocate (rw, 0, at + (int64_t) bytes - 1, 1); while (r != 0 && errno == EINTR);
+  if (r != 0) { close (rw); return false; }
+  const size_t page = (size_t) sysconf (_SC_PAGESIZE);
+  const int64_t map_lo = at & ~(int64_t) (page - 1);
+  const size_t lead = (size_t) (at - map_lo);
+  unsigned char *map = static_cast<unsigned char *> (mmap (NULL, lead + bytes, PROT_READ | PROT_WRITE, MAP_SHARED, rw, map_lo));
+  if (map == MAP_FAILED) { close (rw); return false; }
+  constexpr size_t PIECE = 4u << 20;
+  const unsigned n_copy = std::min (12u, std::max (2u, std::thread::hardware_concurrency () * 3 / 4));
+  const size_t n_pieces = (bytes + PIECE - 1) / PIECE;
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < n_copy && t < n_pieces; t++)
+    pool.emplace_back ([&] {
+      for (size_t k = next.fetch_add (1); k < n_pieces; k = next.fetch_add (1)) {
+        const size_t off = k * PIECE;
+        memcpy (map + lead + off, p + off, std::min (PIECE, bytes - off));
+      }
+    });
+  for (auto &th : pool) th.join ();
+  munmap (map, lead + bytes);
+  close (rw);
+  return true;
+}
+
+// offset < 0: sequential write at the descriptor's position.  Large spans to a regular file go through write_mapped;
+// where that is not possible they are cut into pieces written with pwrite from a few threads.
 int write_all (int fd, const void *buf, size_t bytes, int64_t offset)
 {
   const unsigned char *p = static_cast<const unsigned char *> (buf);
@@ -607,6 +657,10 @@ int write_all (int fd, const void *buf, size_t bytes, int64_t offset)
   constexpr unsigned N_THREADS = 8;       // (page-cache / tmpfs writes are bound by page allocation per thread: 4 -> 8 threads measured)
   if (bytes >= PARALLEL_MIN) {
     const int64_t at = (offset >= 0) ? offset : (int64_t) lseek (fd, 0, SEEK_CUR);
+    if (at >= 0 && write_mapped (fd, p, bytes, at)) {
+      if (offset < 0 && lseek (fd, at + (int64_t) bytes, SEEK_SET) < 0) return fail (GT4GPU_ERR_IO, "lseek failed: %s", strerror (errno));
+      return 0;
+    }
     if (at >= 0) {
       int err[N_THREADS] = {};
       std::vector<std::thread> pool;
@@ -1986,6 +2040,19 @@ struct FileCopyBuffers {
 
 constexpr uint64_t FILE_CHUNK = BOUNCE_BYTES / 12;
 
+// GT4GPU_FILE_TIMING=1: wall-clock seconds of the pipeline's phases on stderr (each counter has one writer thread)
+struct FileTiming {
+  bool on = false;
+  double plan = 0, up_copy = 0, up_wait = 0, up_sync = 0, down_wait = 0, down_write = 0, merge = 0, join_up = 0, join_down = 0, total = 0;
+};
+FileTiming g_ft;
+inline double now_s ()
+{
+  struct timespec ts;
+  clock_gettime (CLOCK_MONOTONIC, &ts);
+  return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
 cudaError_t upload_records (const unsigned char *src, uint64_t n, void *d_aos, uint64_t *d_words, uint32_t *d_counts, FileCopyBuffers &buf,
                             unsigned n_threads, cudaStream_t st)
 {
@@ -1993,14 +2060,19 @@ cudaError_t upload_records (const unsigned char *src, uint64_t n, void *d_aos, u
   int b = 0;
   for (uint64_t done = 0; done < n && e == cudaSuccess; done += FILE_CHUNK, b ^= 1) {
     const uint64_t m = std::min (FILE_CHUNK, n - done);
+    const double t0 = g_ft.on ? now_s () : 0;
     if (done >= 2 * FILE_CHUNK) e = cudaEventSynchronize (buf.ev[b]);
     if (e != cudaSuccess) break;
+    const double t1 = g_ft.on ? now_s () : 0;
     copy_parallel (buf.pinned[b], src + done * 12, m * 12, n_threads);
+    if (g_ft.on) { const double t2 = now_s (); g_ft.up_wait += t1 - t0; g_ft.up_copy += t2 - t1; }
     e = cudaMemcpyAsync (static_cast<unsigned char *> (d_aos) + done * 12, buf.pinned[b], m * 12, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaEventRecord (buf.ev[b], st);
   }
+  const double t3 = g_ft.on ? now_s () : 0;
   if (e == cudaSuccess && n) e = launch_deinterleave (d_aos, n, d_words, d_counts, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize (st);
+  if (g_ft.on) g_ft.up_sync += now_s () - t3;
   return e;
 }
 
@@ -2019,9 +2091,12 @@ int download_records (const uint64_t *d_words, const uint32_t *d_counts, uint64_
   for (uint64_t done = 0; done < n && !rc && e == cudaSuccess; done += FILE_CHUNK, b ^= 1) {
     if (done + FILE_CHUNK < n) enqueue (done + FILE_CHUNK, b ^ 1);
     if (e != cudaSuccess) break;
+    const double t0 = g_ft.on ? now_s () : 0;
     e = cudaEventSynchronize (buf.ev[b]);
     if (e != cudaSuccess) break;
+    const double t1 = g_ft.on ? now_s () : 0;
     rc = write_all (fd, buf.pinned[b], std::min (FILE_CHUNK, n - done) * 12, at + (int64_t) (done * 12));
+    if (g_ft.on) { g_ft.down_wait += t1 - t0; g_ft.down_write += now_s () - t1; }
   }
   cudaStreamSynchronize (st);
   if (!rc && e != cudaSuccess) rc = fail (GT4GPU_ERR_CUDA, "file output: %s", cudaGetErrorString (e));
@@ -2053,6 +2128,9 @@ int gt4gpu_compare2_files (const char *path_a, const char *path_b, int stream_mo
   const uint64_t n_a = ha.n_words, n_b = hb.n_words, total = n_a + n_b;
   for (int s = 0; s < 4; s++) n_out[s] = total_out[s] = 0;
 
+  g_ft = FileTiming ();
+  g_ft.on = getenv ("GT4GPU_FILE_TIMING") != nullptr;
+  const double t_begin = g_ft.on ? now_s () : 0;
   uint64_t part_records = 64ull << 20;
   if (const char *env = getenv ("GT4GPU_HOST_PART_RECORDS")) part_records = strtoull (env, nullptr, 10);
   if (part_records < 1024) part_records = 1024;
@@ -2064,6 +2142,7 @@ int gt4gpu_compare2_files (const char *path_a, const char *path_b, int stream_mo
     const uint64_t sizes[2] = {n_a, n_b};
     if ((rc = gt4gpu_plan_splitters (keys, strides, sizes, 2, n_parts, bounds.data (), nullptr))) return rc;
   }
+  if (g_ft.on) g_ft.plan = now_s () - t_begin;
   const uint64_t *ba = bounds.data (), *bb = bounds.data () + n_parts + 1;
   uint64_t max_a = 0, max_b = 0;
   for (unsigned p = 0; p < n_parts; p++) {
@@ -2138,7 +2217,9 @@ int gt4gpu_compare2_files (const char *path_a, const char *path_b, int stream_mo
       mo[s].caller = true; mo[s].words = st.ow[s]; mo[s].counts = st.oc[s]; mo[s].capacity = cap[s];
     }
     reset_timing ();
+    const double tm0 = g_ft.on ? now_s () : 0;
     rc = merge2_device (DevList{st.wa, st.ca, ba[p + 1] - ba[p]}, DevList{st.wb, st.cb, bb[p + 1] - bb[p]}, prm, ops, countonly != 0, mo);
+    const double tm1 = g_ft.on ? now_s () : 0;
     ms_p += tl_ms_partition; ms_m += tl_ms_merge; nl += tl_launches;
     for (int s = 0; s < 4 && !rc; s++) {
       if (!((ops >> s) & 1u)) continue;
@@ -2147,7 +2228,9 @@ int gt4gpu_compare2_files (const char *path_a, const char *path_b, int stream_mo
       total_out[s] += mo[s].sum;
     }
     if (t_up.joinable ()) t_up.join ();
+    const double tm2 = g_ft.on ? now_s () : 0;
     if (t_down.joinable ()) t_down.join ();
+    if (g_ft.on) { g_ft.merge += tm1 - tm0; g_ft.join_up += tm2 - tm1; g_ft.join_down += now_s () - tm2; }
     if (!rc && rc_down) rc = rc_down;
     if (e_up != cudaSuccess) e = e_up;
   }
@@ -2169,6 +2252,10 @@ int gt4gpu_compare2_files (const char *path_a, const char *path_b, int stream_mo
     h.total_count = total_out[s];
     if ((rc = write_all (out_fd[s], &h, sizeof (h), 0))) return rc;
   }
+  if (g_ft.on)
+    fprintf (stderr, "gt4gpu file pipeline: %u parts, total %.3f s: plan %.3f | main thread: merge %.3f, waits for the upload %.3f, for the download %.3f | "
+                     "upload thread: page cache -> pinned %.3f, waits for H2D %.3f, last H2D + de-interleave %.3f | download thread: waits for D2H %.3f, pwrite %.3f\n",
+             n_parts, now_s () - t_begin, g_ft.plan, g_ft.merge, g_ft.join_up, g_ft.join_down, g_ft.up_copy, g_ft.up_wait, g_ft.up_sync, g_ft.down_wait, g_ft.down_write);
   return 0;
 }
 
