@@ -601,14 +601,13 @@ setop2_fused_kernel (const TileArgs args)
     consumer_sync<NC> ();           // also: every consumer is done reading this stage's inputs
     static_assert (NWARPS <= 32, "one lane per consumer warp");
     const unsigned long long wv = (lane < NWARPS) ? s_wcnt[it & 1][lane] : 0ull;
-    unsigned long long wincl = wv;
-#pragma unroll
-    for (int off = 1; off < NWARPS; off <<= 1) {
-      const unsigned long long t = __shfl_up_sync (0xffffffffu, wincl, off);
-      if (lane >= off) wincl += t;
-    }
-    const unsigned long long tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
-    const unsigned long long before = __shfl_sync (0xffffffffu, wincl - wv, warp) + incl - own;      // exclusive prefixes of this thread
+    // four warp reductions (REDUX) over the 32-bit halves instead of a shuffle scan of the 64-bit words: the 16-bit fields
+    // cannot carry into each other (a tile holds fewer than 2^16 slots)
+    const unsigned long long wb = (lane < warp) ? wv : 0ull;
+    const unsigned long long tile_cnt = (unsigned long long) __reduce_add_sync (0xffffffffu, (unsigned) wv)
+                                      | ((unsigned long long) __reduce_add_sync (0xffffffffu, (unsigned) (wv >> 32)) << 32);
+    const unsigned long long before = ((unsigned long long) __reduce_add_sync (0xffffffffu, (unsigned) wb)
+                                       | ((unsigned long long) __reduce_add_sync (0xffffffffu, (unsigned) (wb >> 32)) << 32)) + incl - own;      // exclusive prefixes of this thread
     int tc[4], pos[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {

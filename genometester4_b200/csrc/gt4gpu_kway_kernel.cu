@@ -446,14 +446,9 @@ kway_tile_kernel (const KwayArgs args)
     consumer_sync<NC> ();
 #pragma unroll
     for (int q = 0; q < NL / 2; q++) {
-      uint32_t w = (lane < NWARPS) ? s_wtot[lane][q] : 0u;
-      const uint32_t own = w;
-#pragma unroll
-      for (int off = 1; off < NWARPS; off <<= 1) {
-        const uint32_t t = __shfl_up_sync (0xffffffffu, w, off);
-        if (lane >= off) w += t;
-      }
-      pk[q] += __shfl_sync (0xffffffffu, w - own, warp);
+      // (the packed 16-bit halves cannot carry into each other: a tile holds fewer than 2^16 records)
+      const uint32_t w = (lane < warp) ? s_wtot[lane][q] : 0u;          // warp < NWARPS
+      pk[q] += __reduce_add_sync (0xffffffffu, w);                      // one REDUX: total of the warps before this one
     }
     const long long c2 = prof ? clock64 () : 0;
     int idx[NL], end[NL];
@@ -527,14 +522,8 @@ kway_tile_kernel (const KwayArgs args)
     consumer_sync<NC> ();             // also: every consumer is done reading this stage's slices
     static_assert (NWARPS <= 32, "one lane per consumer warp");
     const int wv = (lane < NWARPS) ? s_wcnt[it & 1][lane] : 0;
-    int wincl = wv;
-#pragma unroll
-    for (int off = 1; off < NWARPS; off <<= 1) {
-      const int t = __shfl_up_sync (0xffffffffu, wincl, off);
-      if (lane >= off) wincl += t;
-    }
-    const int tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
-    const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
+    const int tile_cnt = (int) __reduce_add_sync (0xffffffffu, (unsigned) wv);
+    const int warp_prefix = (int) __reduce_add_sync (0xffffffffu, (unsigned) (lane < warp ? wv : 0));
     if (tid == 0) {
       s_mail[s].tile = tile_id;
       s_mail[s].cnt = tile_cnt;

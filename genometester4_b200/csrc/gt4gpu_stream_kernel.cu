@@ -46,6 +46,9 @@ constexpr int STORE_WARPS = GT4_STORE_WARPS;
 #ifndef GT4_INTERIOR_MERGE
 #define GT4_INTERIOR_MERGE 1      // full tiles away from the ends of the lists take the merge loop without cursor bounds
 #endif
+#ifndef GT4_REDUX_SCAN
+#define GT4_REDUX_SCAN 1
+#endif
 #ifndef GT4_STATIC_TILES
 #define GT4_STATIC_TILES 0
 #endif
@@ -569,6 +572,12 @@ setop2_stream_kernel (const TileArgs args)
     // prefix over the (at most 32) warp totals with one more shuffle scan instead of a loop per thread
     static_assert (NWARPS <= 32, "one lane per consumer warp");
     const int wv = (lane < NWARPS) ? s_wcnt[it & 1][lane] : 0;
+#if GT4_REDUX_SCAN
+    // two warp reductions (REDUX) instead of a shuffle scan over the warp totals: every thread only needs the tile total and
+    // the total of the warps before its own
+    const int tile_cnt = (int) __reduce_add_sync (0xffffffffu, (unsigned) wv);
+    const int warp_prefix = (int) __reduce_add_sync (0xffffffffu, (unsigned) (lane < warp ? wv : 0));
+#else
     int wincl = wv;
 #pragma unroll
     for (int off = 1; off < NWARPS; off <<= 1) {
@@ -577,6 +586,7 @@ setop2_stream_kernel (const TileArgs args)
     }
     const int tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
     const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
+#endif
     if (tid == 0) {
       s_mail[s].tile = m.tile;
       s_mail[s].cnt = tile_cnt;

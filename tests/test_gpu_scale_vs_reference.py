@@ -77,6 +77,15 @@ def test_two_lists_5e7_byte_identical_to_reference(work, oracle):
         assert ref_files and my_files == ref_files, (flags, ref_files, my_files)
         (_, ref_out), (_, my_out) = _both(oracle, [a, b, *flags, "--count_only"], work, tag + "_co")
         assert my_out == ref_out and b"NUnique" in ref_out, (flags, ref_out, my_out)
+        if tag == "ui":
+            # the same files from three key-range shards (one process each, sharing the device on a one-GPU box): every shard
+            # writes its slice of each output at an arbitrary record offset while the others write theirs
+            run = work / "ui_shards"
+            run.mkdir()
+            r = subprocess.run([str(_lib.cli_path()), str(a), str(b), *flags, "--gpus", "3"], cwd=run, capture_output=True, timeout=900)
+            assert r.returncode == 0, r.stderr[-500:]
+            assert _outputs(run) == ref_files
+            shutil.rmtree(run)
     a.unlink()
     b.unlink()
 
