@@ -264,6 +264,31 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
       first = false;
       args.stream0 = s;
       args.p.ops = 1u << s;
+      // Sparse outputs merge 12 % faster through the side-buffer variant of the kernel, dense ones 20 % slower, and the
+      // density is a property of the data: count the survivors of every 64th tile first (1.6 % of the merge's time)
+      // when the call is big enough for that to pay.
+      args.side_hint = 0;
+      constexpr uint64_t SAMPLE_STRIDE = 64, SAMPLE_MIN_TILES = 8192;
+      if (!countonly && n_tiles >= SAMPLE_MIN_TILES && stream_side_capable (args.p, s, g_ctx.stream_consumers, g_ctx.stream_items)) {
+        CallHeader *h2 = nullptr;
+        const size_t h2_bytes = (sizeof (CallHeader) + 255) & ~(size_t) 255;
+        int rc2 = dev_alloc ((void **) &h2, h2_bytes);
+        if (rc2) return rc2;
+        struct H2Guard { CallHeader *p; ~H2Guard () { dev_free (p); } } h2_guard{h2};
+        CU (cudaMemsetAsync (h2, 0, h2_bytes, st));
+        TileArgs sample = args;
+        sample.hdr = h2;
+        sample.tile_stride = (uint32_t) SAMPLE_STRIDE;
+        CU (launch_setop2_stream (sample, g_ctx.stream_consumers, g_ctx.stream_items, true, g_ctx.sm_count, st));
+        n_launches += 1;
+        CallHeader hs;
+        CU (cudaMemcpyAsync (&hs, h2, sizeof (hs), cudaMemcpyDeviceToHost, st));
+        CU (cudaStreamSynchronize (st));
+        uint64_t kept = 0;
+        for (int k = 0; k < TOTAL_SLOTS; k++) kept += hs.totals[s][k][0];
+        const uint64_t sampled_slots = ((n_tiles + SAMPLE_STRIDE - 1) / SAMPLE_STRIDE) * tile;
+        args.side_hint = (double) kept <= 0.27 * (double) sampled_slots;       // (a side buffer holds a third of a tile's slots)
+      }
       CU (launch_setop2_stream (args, g_ctx.stream_consumers, g_ctx.stream_items, countonly, g_ctx.sm_count, st));
       n_launches += 1;
     }
@@ -1074,6 +1099,10 @@ int gt4gpu_set_option (const char *name, int value)
   }
   if (!strcmp (name, "use_fused")) {
     g_ctx.use_fused = value != 0;
+    return 0;
+  }
+  if (!strcmp (name, "stream_side")) {       // 0: intersections / differences take the plain stream kernel too
+    g_stream_side = value < 0 ? 0 : value > 2 ? 2 : value;
     return 0;
   }
   if (!strcmp (name, "use_stream_kernel")) {

@@ -106,6 +106,12 @@ __device__ __forceinline__ void mbar_arrive (uint64_t *bar)
   asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (bar)) : "memory");
 }
 
+// several arrivals at once (one thread standing in for `count` arrivers)
+__device__ __forceinline__ void mbar_arrive_n (uint64_t *bar, uint32_t count)
+{
+  asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(count) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive_expect_tx (uint64_t *bar, uint32_t bytes)
 {
   asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32 (bar)), "r"(bytes) : "memory");

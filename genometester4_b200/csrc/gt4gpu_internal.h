@@ -45,6 +45,8 @@ struct TileArgs {
   uint64_t out_capacity[4];
   CallHeader *hdr;
   uint64_t *desc;              // look-back descriptors, [stream slot][n_tiles]
+  uint32_t tile_stride;        // stream kernel, count-only: > 1 visits every tile_stride-th tile only (density sample)
+  int side_hint;               // stream kernel: the output is sparse, use the side-buffer variant where it exists
   int stream0;                 // the single requested stream when the 1-stream kernel is used
   int debug;                   // experiments only (GT4GPU_DEBUG): bit 0 = skip the look-back (WRONG output offsets)
   SetOpParams p;
@@ -64,6 +66,9 @@ cudaError_t launch_setop2 (const TileArgs &args, TileShape shape, int n_streams,
 // second-generation single-output kernel (gt4gpu_stream_kernel.cu): persistent, warp-specialised, TMA-staged;
 // tiles are consumers * items merged slots
 bool stream_shape_supported (int consumers, int items);
+extern int g_stream_side;
+// does a side-buffer variant exist for this output (and is it enabled)?
+bool stream_side_capable (const SetOpParams &p, int stream, int consumers, int items);
 cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items, bool count_only, int sm_count, cudaStream_t st);
 
 // multi-output kernel on the same pipeline (gt4gpu_fused_kernel.cu): one read of the lists, up to four outputs.

@@ -71,7 +71,7 @@ constexpr uint64_t TILE_END = ~0ull;
 using namespace dev;
 
 // NC consumer threads (warps 0 .. NC/32-1), then the producer warp, the look-back warp and the store warps
-template <int NC, int VT, int S>
+template <int NC, int VT, int S, bool SIDE = false>
 struct StreamCfg {
   static constexpr int CONSUMERS = NC;
   static constexpr int STAGES = S;
@@ -92,7 +92,11 @@ struct StreamCfg {
   static constexpr int KSLOTS = (TILE + VT + 16 + 1) & ~1;
   static constexpr int CSLOTS = (TILE + VT + 28 + 3) & ~3;
   static constexpr size_t STAGE_BYTES = (size_t) KSLOTS * 8 + (size_t) CSLOTS * 4;
-  static constexpr size_t SMEM_BYTES = S * STAGE_BYTES;
+  // SIDE: sparse outputs (intersections, differences) are compacted into a small side buffer per stage, so the stage goes
+  // back to the producer right after the merge instead of waiting for the tile's offset and store
+  static constexpr int SIDE_CAP = SIDE ? 1536 : 0;          // survivors a side buffer holds; fuller tiles keep their stage
+  static constexpr size_t SIDE_BYTES = (size_t) SIDE_CAP * 12;
+  static constexpr size_t SMEM_BYTES = S * (STAGE_BYTES + SIDE_BYTES);
 };
 
 struct StageMeta {
@@ -107,6 +111,7 @@ struct Mailbox {
   uint64_t tile;
   uint64_t base;     // exclusive prefix of the tile's output count (written by the look-back warp)
   int cnt;           // the tile's output count (written by consumer thread 0)
+  int side;          // SIDE kernels: 1 = the survivors sit in the stage's side buffer, 0 = at the front of the stage itself
 };
 
 // All 32 lanes of the look-back warp; returns the exclusive prefix of `aggregate`.
@@ -140,11 +145,12 @@ __device__ __forceinline__ uint64_t lookback_with_stats (uint64_t *desc, uint64_
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-template <int NC, int VT, int S, int FAST, bool COUNT_ONLY>
-__global__ void __launch_bounds__ (StreamCfg<NC, VT, S>::NTHREADS, StreamCfg<NC, VT, S>::MIN_CTAS)
+template <int NC, int VT, int S, int FAST, bool COUNT_ONLY, bool SIDE = false>
+__global__ void __launch_bounds__ (StreamCfg<NC, VT, S, SIDE>::NTHREADS, StreamCfg<NC, VT, S, SIDE>::MIN_CTAS)
 setop2_stream_kernel (const TileArgs args)
 {
-  using Cfg = StreamCfg<NC, VT, S>;
+  using Cfg = StreamCfg<NC, VT, S, SIDE>;
+  static_assert (!(SIDE && COUNT_ONLY), "the side buffers are an output path");
   constexpr int TILE = Cfg::TILE;
   constexpr int STAGES = S;
   constexpr int NWARPS = NC / 32;
@@ -161,7 +167,8 @@ setop2_stream_kernel (const TileArgs args)
   __shared__ __align__ (8) uint64_t bar_comp[STAGES];    // consumers -> store warps: survivors compacted
   __shared__ __align__ (8) uint64_t bar_agg[STAGES];     // consumers -> look-back: tile count posted
   __shared__ __align__ (8) uint64_t bar_base[STAGES];    // look-back -> store warps: global offset ready
-  __shared__ __align__ (8) uint64_t bar_empty[STAGES];   // store warps (count-only: consumers) -> producer
+  __shared__ __align__ (8) uint64_t bar_empty[STAGES];   // store warps (count-only: consumers; SIDE, sparse tile: consumer thread 0) -> producer
+  __shared__ __align__ (8) uint64_t bar_done[STAGES];    // SIDE: store warps -> consumers: the slot's tile has been stored
   __shared__ StageMeta s_meta[STAGES];
   __shared__ Mailbox s_mail[STAGES];
   __shared__ int s_split[STAGES][NSPLIT];
@@ -182,6 +189,7 @@ setop2_stream_kernel (const TileArgs args)
       mbar_init (&bar_agg[s], 1);
       mbar_init (&bar_base[s], 1);
       mbar_init (&bar_empty[s], COUNT_ONLY ? NWARPS : STORE_WARPS);
+      mbar_init (&bar_done[s], STORE_WARPS);
     }
     s_n_iter = 0xffffffffu;
     fence_mbar_init ();
@@ -190,6 +198,8 @@ setop2_stream_kernel (const TileArgs args)
 
   auto stage_keys = [&] (int s) { return reinterpret_cast<uint64_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES); };
   auto stage_cnts = [&] (int s) { return reinterpret_cast<uint32_t *> (smem_raw + (size_t) s * Cfg::STAGE_BYTES + (size_t) Cfg::KSLOTS * 8); };
+  auto side_keys = [&] (int s) { return reinterpret_cast<uint64_t *> (smem_raw + (size_t) STAGES * Cfg::STAGE_BYTES + (size_t) s * Cfg::SIDE_BYTES); };
+  auto side_cnts = [&] (int s) { return reinterpret_cast<uint32_t *> (smem_raw + (size_t) STAGES * Cfg::STAGE_BYTES + (size_t) s * Cfg::SIDE_BYTES + (size_t) Cfg::SIDE_CAP * 8); };
 
   // ============================================================================ producer
   if (warp == PRODUCER_WARP) {
@@ -211,15 +221,16 @@ setop2_stream_kernel (const TileArgs args)
 #if GT4_STATIC_TILES
     // experiment: tile = round * grid + CTA (needs every CTA of the grid resident; fewer look-back polls, no balancing)
     uint64_t static_round = 0;
-#define GT4_CLAIM_TICKET() ((uint64_t) blockIdx.x + (static_round++) * (uint64_t) gridDim.x)
+#define GT4_CLAIM_TICKET() (((uint64_t) blockIdx.x + (static_round++) * (uint64_t) gridDim.x) * tile_stride)
 #else
-#define GT4_CLAIM_TICKET() ((uint64_t) atomicAdd (&args.hdr->ticket, 1u))
+#define GT4_CLAIM_TICKET() ((uint64_t) atomicAdd (&args.hdr->ticket, 1u) * tile_stride)
 #endif
+    const uint64_t tile_stride = args.tile_stride ? args.tile_stride : 1;      // > 1: a count-only pass over a sample of the tiles
     uint64_t nxt = GT4_CLAIM_TICKET ();
     uint64_t nxt_lo = 0, nxt_hi = 0;
     if (nxt < n_tiles) { nxt_lo = args.part[nxt]; nxt_hi = args.part[nxt + 1]; }
     // L2 prefetch of the tiles the grid will claim about two rounds from now (co-ranks loaded one iteration early)
-    const uint64_t pf_dist = gridDim.x;
+    const uint64_t pf_dist = gridDim.x * tile_stride;
     uint64_t pf_tile = nxt + pf_dist, pf_lo = 0, pf_hi = 0;
     if (pf_tile < n_tiles) { pf_lo = args.part[pf_tile]; pf_hi = args.part[pf_tile + 1]; }
     int s = 0;
@@ -453,8 +464,9 @@ setop2_stream_kernel (const TileArgs args)
       helper_wait (&bar_base[s], ph);
       const uint64_t base = s_mail[s].base;
       const int cnt = s_mail[s].cnt;
-      const uint64_t *sk = stage_keys (s);
-      const uint32_t *sc = stage_cnts (s);
+      const bool from_side = SIDE && s_mail[s].side != 0;
+      const uint64_t *sk = from_side ? side_keys (s) : stage_keys (s);
+      const uint32_t *sc = from_side ? side_cnts (s) : stage_cnts (s);
       if (args.debug & 8) {
         // experiment: no stores
       } else if (base + (uint64_t) cnt > args.out_capacity[stream]) {
@@ -485,7 +497,10 @@ setop2_stream_kernel (const TileArgs args)
       fence_proxy_async ();          // generic accesses to the stage before the async proxy (TMA) refills it
 #endif
       __syncwarp ();
-      if (lane == 0) mbar_arrive (&bar_empty[s]);
+      if (lane == 0) {
+        if (!from_side) mbar_arrive (&bar_empty[s]);       // (a tile in a side buffer gave its stage back long ago)
+        if (SIDE) mbar_arrive (&bar_done[s]);
+      }
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     return;
@@ -507,6 +522,7 @@ setop2_stream_kernel (const TileArgs args)
       if (COUNT_ONLY) break;
       // END markers arrive on S consecutive stages; pass each one on to that stage's look-back warp
       // (and the first one to the store warps)
+      if (SIDE) mbar_wait (&bar_done[s], ph ^ 1u);        // the store warps may still be reading the slot's previous mailbox
       if (tid == 0) {
         if (it < s_n_iter) s_n_iter = it;
         s_mail[s].tile = TILE_END;
@@ -587,24 +603,37 @@ setop2_stream_kernel (const TileArgs args)
     const int tile_cnt = __shfl_sync (0xffffffffu, wincl, NWARPS - 1);
     const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
 #endif
+    const bool to_side = SIDE && tile_cnt <= Cfg::SIDE_CAP;
+    if (SIDE) mbar_wait (&bar_done[s], ph ^ 1u);      // the slot's previous tile has been stored: its mailbox and side buffer are free
     if (tid == 0) {
       s_mail[s].tile = m.tile;
       s_mail[s].cnt = tile_cnt;
+      s_mail[s].side = to_side ? 1 : 0;
       mbar_arrive (&bar_agg[s]);    // the look-back warp takes it from here
     }
+    uint64_t *dk = sk;
+    uint32_t *dc = sc;
+    if (to_side) {
+      // few survivors: they go to the stage's side buffer and the stage itself returns to the producer NOW (every consumer
+      // read its inputs before the named barrier above), one look-back + store earlier than otherwise
+      if (tid == 0) mbar_arrive_n (&bar_empty[s], STORE_WARPS);      // standing in for the store warps, which never touch this stage
+      dk = side_keys (s);
+      dc = side_cnts (s);
+    }
 
-    // compact this tile's survivors to the front of its own stage buffer, then hand it to the store warps
+    // compact this tile's survivors (to the front of its own stage buffer unless to_side), then hand them to the store warps
     int pos = warp_prefix + incl - cnt;
 #pragma unroll
     for (int sl = 0; sl < VT; sl++) {
       if ((mask >> sl) & 1u) {
-        sk[pos] = o_key[sl];
-        sc[pos] = o_freq[sl];
+        dk[pos] = o_key[sl];
+        dc[pos] = o_freq[sl];
         pos += 1;
       }
     }
     __syncwarp ();
     if (lane == 0) mbar_arrive (&bar_comp[s]);
+
     if (prof) { const long long c5 = clock64 (); t_scan += c4 - c3; t_scatter += c5 - c4; }
     if (++s == STAGES) { s = 0; ph ^= 1u; }
   }
@@ -636,13 +665,13 @@ setop2_stream_kernel (const TileArgs args)
 }
 
 // ---- launch ------------------------------------------------------------------------------------
-template <int NC, int VT, int S, int FAST, bool CO>
+template <int NC, int VT, int S, int FAST, bool CO, bool SIDE = false>
 cudaError_t launch_stream_one (const TileArgs &args, int sm_count, cudaStream_t st)
 {
-  using Cfg = StreamCfg<NC, VT, S>;
+  using Cfg = StreamCfg<NC, VT, S, SIDE>;
   constexpr int NTHREADS = Cfg::NTHREADS;
   static int ctas_per_sm = 0;      // benign race: idempotent
-  auto kernel = setop2_stream_kernel<NC, VT, S, FAST, CO>;
+  auto kernel = setop2_stream_kernel<NC, VT, S, FAST, CO, SIDE>;
   if (ctas_per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -653,7 +682,8 @@ cudaError_t launch_stream_one (const TileArgs &args, int sm_count, cudaStream_t 
     ctas_per_sm = occ;
   }
   uint64_t grid = (uint64_t) sm_count * ctas_per_sm;
-  if (grid > args.n_tiles) grid = args.n_tiles;
+  const uint64_t n_claims = args.tile_stride > 1 ? (args.n_tiles + args.tile_stride - 1) / args.tile_stride : args.n_tiles;
+  if (grid > n_claims) grid = n_claims;
   kernel<<<(unsigned) grid, NTHREADS, Cfg::SMEM_BYTES, st>>> (args);
   return cudaGetLastError ();
 }
@@ -674,6 +704,15 @@ cudaError_t launch_stream_fast (const TileArgs &args, int fast, int sm_count, cu
 
 }  // namespace
 
+int g_stream_side = 1;      // option "stream_side": 1 = sparse outputs (TileArgs::side_hint) take the side-buffer variant, 2 = everything it is built for (measurements), 0 = never
+
+bool stream_side_capable (const SetOpParams &p, int stream, int consumers, int items)
+{
+  if (g_stream_side != 1 || consumers != 512 || items != 9) return false;
+  const int fast = select_fast_path (p, stream);
+  return fast == FAST_I_MIN || fast == FAST_D_SUB || fast == FAST_D2_SUB || fast == FAST_NI_MIN;
+}
+
 // supported (consumer threads, items per thread, stages) triples; the stage count is fixed per shape by shared memory
 #define GT4GPU_STREAM_SHAPES(X) X (256, 7, 5) X (256, 9, 4) X (256, 11, 3) X (384, 9, 5) X (384, 11, 4) X (512, 7, 5) X (512, 9, 4) X (512, 11, 3)
 
@@ -689,6 +728,17 @@ cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items
 {
   if (args.n_tiles == 0) return cudaSuccess;
   const int fast = select_fast_path (args.p, args.stream0);
+  // outputs that are sparse as a rule (intersections, differences) at the default tile: the side-buffer variant, 3 stages
+  if (!count_only && consumers == 512 && items == 9 && (g_stream_side == 2 || (g_stream_side == 1 && args.side_hint))) {
+    if (g_stream_side == 2 && fast == FAST_U_ADD) return launch_stream_one<512, 9, 3, FAST_U_ADD, false, true> (args, sm_count, st);      // (measurements)
+    switch (fast) {
+    case FAST_I_MIN:  return launch_stream_one<512, 9, 3, FAST_I_MIN, false, true> (args, sm_count, st);
+    case FAST_D_SUB:  return launch_stream_one<512, 9, 3, FAST_D_SUB, false, true> (args, sm_count, st);
+    case FAST_D2_SUB: return launch_stream_one<512, 9, 3, FAST_D2_SUB, false, true> (args, sm_count, st);
+    case FAST_NI_MIN: return launch_stream_one<512, 9, 3, FAST_NI_MIN, false, true> (args, sm_count, st);
+    default: break;
+    }
+  }
 #define X(NC, VT, S)                                                                                        \
   if (consumers == NC && items == VT) return count_only ? launch_stream_fast<NC, VT, S, true> (args, fast, sm_count, st) \
                                                         : launch_stream_fast<NC, VT, S, false> (args, fast, sm_count, st);

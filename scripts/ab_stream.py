@@ -11,6 +11,8 @@ from genometester4_b200 import synth
 n = float(sys.argv[1]) if len(sys.argv) > 1 else 1e9
 ops = sys.argv[2:] or ["union"]
 g.init(0); g.set_stream(torch.cuda.current_stream().cuda_stream)
+if os.environ.get("STREAM_SIDE") is not None:
+    g.set_option("stream_side", int(os.environ["STREAM_SIDE"]))
 m = int(round(1.5 * n))
 (wa, ca), (wb, cb) = synth.pair_torch(42, 25, m, 0, m, 1 / 3, 1 / 3)
 na, nb = wa.numel(), wb.numel()

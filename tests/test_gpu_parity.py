@@ -147,6 +147,48 @@ def test_stream_kernel_every_shape_rule_and_semantics(g, oracle, shape):
         g.set_option("stream_shape", 51209)
 
 
+def test_stream_kernel_side_buffer_variant_forced(g, oracle):
+    """The side-buffer variant of the stream kernel (3 stages + a side buffer per stage; sparse tiles give their stage back
+    right after the merge, fuller tiles keep it) is chosen from a density sample on big calls only; here it is forced
+    (stream_side = 2) on inputs of hundreds of tiles whose outputs are sparse, mixed and dense (identical lists: every
+    tile overflows its side buffer), for the four outputs, cut-offs, and the N-list intersection chain."""
+    g.set_option("stream_shape", 51209)
+    g.set_option("stream_side", 2)
+    try:
+        for seed, (na, nb, both), kind in ((21, (300_001, 250_003, 120_000), "tail"), (22, (400_000, 400_000, 400_000), "small"),
+                                           (23, (500_000, 480_000, 20_000), "tail"), (24, (3, 200_001, 2), "tail"), (25, (150_000, 7, 0), "huge"),
+                                           (26, (5, 3, 2), "tail"), (27, (700_000, 100_000, 100_000), "small")):
+            a, b = make_pair(seed, na, nb, both, 25, kind)
+            la, lb = g.WordList.from_arrays(*a, 25), g.WordList.from_arrays(*b, 25)
+            sa, sb = oracle.SList(*a, 25), oracle.SList(*b, 25)
+            for cutoff in (1, 3):
+                want = oracle.compare2(sa, sb, union=True, intrsec=True, diff=True, ddiff=True, cutoff=cutoff)
+                for s, kw in (("union", dict(find_union=1)), ("intrsec", dict(find_intrsec=1)), ("diff1", dict(find_diff=1)), ("diff2", dict(find_ddiff=1))):
+                    r = g.compare_wordmaps(la, lb, cutoff=cutoff, **kw)[s]
+                    w, c = r.to_host()
+                    assert np.array_equal(w, want[s].words) and np.array_equal(c, want[s].counts), (seed, cutoff, s)
+                    assert (r.n_words, r.total_count) == (want[s].n_words, want[s].total_count)
+        # N-list intersection: a chain of two-list links (rule min with the guard), every link through the variant
+        g.set_option("use_kway", 0)
+        rng = np.random.default_rng(5)
+        base = np.unique(rng.integers(0, 1 << 50, size=600_000, dtype=np.uint64))
+        lists, slists = [], []
+        for j in range(4):
+            keep = rng.random(base.size) < (0.9 if j < 2 else 0.5)
+            w = base[keep]
+            c = rng.integers(1, 7, size=w.size, dtype=np.uint32)
+            lists.append(g.WordList.from_arrays(w, c, 25))
+            slists.append(oracle.SList(w, c, 25))
+        for cutoff in (1, 2):
+            rc, want = oracle.intersect_multi(slists, cutoff=cutoff)
+            got = g.intersect_multi(lists, cutoff=cutoff)
+            w, c = got.to_host()
+            assert rc == 0 and np.array_equal(w, want.words) and np.array_equal(c, want.counts), cutoff
+    finally:
+        g.set_option("stream_side", 1)
+        g.set_option("use_kway", 1)
+
+
 def test_stream_kernel_misaligned_device_views(g, oracle):
     """Caller-owned device arrays that start at every 8/4-byte phase of a 16-byte line (the TMA
     bulk copies over-fetch to 16-byte boundaries and the kernel must shift accordingly)."""
