@@ -116,8 +116,12 @@ const char *gt4gpu_last_error (void);
 /* Kernel tile shape: threads per CTA and merged items per thread.  Unsupported pairs fail with GT4GPU_ERR_ARG. */
 int gt4gpu_set_tile (int threads, int items_per_thread);
 /* Tuning knobs: "stream_shape" (consumer threads per CTA * 100 + merged items per thread of the single-output kernel,
- * e.g. 51209; also settable one at a time as "stream_consumers" / "stream_items") and
- * "use_stream_kernel" (0 routes single-output merges through the multi-output tile kernel as well). */
+ * e.g. 51209; also settable one at a time as "stream_consumers" / "stream_items"),
+ * "use_stream_kernel" (0 routes single-output merges through the multi-output tile kernel as well),
+ * "use_fused" (0: several outputs take one pass of the single-output kernel each instead of the one-read kernel),
+ * "use_kway" (0: N-list calls run as a tree / chain of two-list merges, 1: unions take the single-pass kernel,
+ * 2: intersections too) and "stream_side" (0: sparse outputs never take the side-buffer variant of the single-output
+ * kernel, 1: when a density sample of the call says so, 2: always where the variant exists).  None of them changes a result. */
 int gt4gpu_set_option (const char *name, int value);
 /* Device time of the most recent merge call on this thread, from CUDA events on the launch stream:
  * partition kernel, tile kernel, and the launch count (each may be NULL). */
