@@ -288,7 +288,8 @@ int merge2_device (const DevList &a, const DevList &b, const SetOpParams &p, uin
         uint64_t kept = 0;
         for (int k = 0; k < TOTAL_SLOTS; k++) kept += hs.totals[s][k][0];
         const uint64_t sampled_slots = ((n_tiles + SAMPLE_STRIDE - 1) / SAMPLE_STRIDE) * tile;
-        args.side_hint = (double) kept <= 0.27 * (double) sampled_slots;       // (a side buffer holds a third of a tile's slots)
+        // (a side buffer holds a third of a tile's slots in the three-stage variant, 61 % in the two-stage one)
+        args.side_hint = (double) kept <= 0.27 * (double) sampled_slots ? 1 : (double) kept <= 0.56 * (double) sampled_slots ? 2 : 0;
       }
       CU (launch_setop2_stream (args, g_ctx.stream_consumers, g_ctx.stream_items, countonly, g_ctx.sm_count, st));
       n_launches += 1;
@@ -1015,7 +1016,7 @@ int gt4gpu_set_option (const char *name, int value)
     return 0;
   }
   if (!strcmp (name, "stream_side")) {       // 0: intersections / differences take the plain stream kernel too
-    g_stream_side = value < 0 ? 0 : value > 2 ? 2 : value;
+    g_stream_side = value < 0 ? 0 : value > 3 ? 3 : value;
     return 0;
   }
   if (!strcmp (name, "use_stream_kernel")) {

@@ -71,15 +71,18 @@ constexpr uint64_t TILE_END = ~0ull;
 using namespace dev;
 
 // NC consumer threads (warps 0 .. NC/32-1), then the producer warp, the look-back warp and the store warps
-template <int NC, int VT, int S, bool SIDE = false>
+template <int NC, int VT, int S, int SIDE = 0>
 struct StreamCfg {
   static constexpr int CONSUMERS = NC;
   static constexpr int STAGES = S;
   static constexpr int PRODUCER_WARP = NC / 32;
   static constexpr int SPLITTER_WARP = NC / 32 + 1;
-  static constexpr int LOOKBACK_WARP0 = NC / 32 + 2;          // one look-back warp per stage
-  static constexpr int STORE_WARP0 = LOOKBACK_WARP0 + S;
-  static constexpr int NTHREADS = NC + 64 + 32 * S + 32 * STORE_WARPS;
+  // output slots: mailbox + barriers (+ side buffer) of a tile between the end of its merge and the end of its store.  One
+  // per stage, except SIDE == 2: two stages, three slots with bigger side buffers
+  static constexpr int OUT_SLOTS = (SIDE == 2) ? 3 : S;
+  static constexpr int LOOKBACK_WARP0 = NC / 32 + 2;          // one look-back warp per output slot
+  static constexpr int STORE_WARP0 = LOOKBACK_WARP0 + OUT_SLOTS;
+  static constexpr int NTHREADS = NC + 64 + 32 * OUT_SLOTS + 32 * STORE_WARPS;
 #ifndef GT4_SPLIT_POINTS
 #define GT4_SPLIT_POINTS 32
 #endif
@@ -94,9 +97,11 @@ struct StreamCfg {
   static constexpr size_t STAGE_BYTES = (size_t) KSLOTS * 8 + (size_t) CSLOTS * 4;
   // SIDE: sparse outputs (intersections, differences) are compacted into a small side buffer per stage, so the stage goes
   // back to the producer right after the merge instead of waiting for the tile's offset and store
-  static constexpr int SIDE_CAP = SIDE ? 1536 : 0;          // survivors a side buffer holds; fuller tiles keep their stage
+  // (SIDE == 1: three stages, a side buffer of a third of a tile per stage; SIDE == 2: two stages, three side buffers of 61 %
+  // of a tile for outputs of medium density)
+  static constexpr int SIDE_CAP = SIDE == 1 ? 1536 : SIDE == 2 ? 2816 : 0;          // survivors a side buffer holds; fuller tiles keep their stage
   static constexpr size_t SIDE_BYTES = (size_t) SIDE_CAP * 12;
-  static constexpr size_t SMEM_BYTES = S * (STAGE_BYTES + SIDE_BYTES);
+  static constexpr size_t SMEM_BYTES = S * STAGE_BYTES + OUT_SLOTS * SIDE_BYTES;
 };
 
 struct StageMeta {
@@ -111,7 +116,8 @@ struct Mailbox {
   uint64_t tile;
   uint64_t base;     // exclusive prefix of the tile's output count (written by the look-back warp)
   int cnt;           // the tile's output count (written by consumer thread 0)
-  int side;          // SIDE kernels: 1 = the survivors sit in the stage's side buffer, 0 = at the front of the stage itself
+  int side;          // SIDE kernels: 1 = the survivors sit in the slot's side buffer, 0 = at the front of the stage itself
+  int stage;         // the stage the tile was merged in
 };
 
 // All 32 lanes of the look-back warp; returns the exclusive prefix of `aggregate`.
@@ -145,12 +151,14 @@ __device__ __forceinline__ uint64_t lookback_with_stats (uint64_t *desc, uint64_
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-template <int NC, int VT, int S, int FAST, bool COUNT_ONLY, bool SIDE = false>
+template <int NC, int VT, int S, int FAST, bool COUNT_ONLY, int SIDE = 0>
 __global__ void __launch_bounds__ (StreamCfg<NC, VT, S, SIDE>::NTHREADS, StreamCfg<NC, VT, S, SIDE>::MIN_CTAS)
 setop2_stream_kernel (const TileArgs args)
 {
   using Cfg = StreamCfg<NC, VT, S, SIDE>;
   static_assert (!(SIDE && COUNT_ONLY), "the side buffers are an output path");
+  constexpr int QS = Cfg::OUT_SLOTS;
+  constexpr bool ONE_END = COUNT_ONLY || QS != S;      // the producer sends one END marker (else one per stage)
   constexpr int TILE = Cfg::TILE;
   constexpr int STAGES = S;
   constexpr int NWARPS = NC / 32;
@@ -164,13 +172,13 @@ setop2_stream_kernel (const TileArgs args)
   extern __shared__ __align__ (128) unsigned char smem_raw[];
   __shared__ __align__ (8) uint64_t bar_full[STAGES];    // producer -> consumers: slices have landed (TMA tx)
   __shared__ __align__ (8) uint64_t bar_split[STAGES];   // splitter -> consumers: coarse co-ranks ready (implies full)
-  __shared__ __align__ (8) uint64_t bar_comp[STAGES];    // consumers -> store warps: survivors compacted
-  __shared__ __align__ (8) uint64_t bar_agg[STAGES];     // consumers -> look-back: tile count posted
-  __shared__ __align__ (8) uint64_t bar_base[STAGES];    // look-back -> store warps: global offset ready
+  __shared__ __align__ (8) uint64_t bar_comp[QS];        // consumers -> store warps: survivors compacted
+  __shared__ __align__ (8) uint64_t bar_agg[QS];         // consumers -> look-back: tile count posted
+  __shared__ __align__ (8) uint64_t bar_base[QS];        // look-back -> store warps: global offset ready
   __shared__ __align__ (8) uint64_t bar_empty[STAGES];   // store warps (count-only: consumers; SIDE, sparse tile: consumer thread 0) -> producer
-  __shared__ __align__ (8) uint64_t bar_done[STAGES];    // SIDE: store warps -> consumers: the slot's tile has been stored
+  __shared__ __align__ (8) uint64_t bar_done[QS];        // SIDE: store warps -> consumers: the slot's tile has been stored
   __shared__ StageMeta s_meta[STAGES];
-  __shared__ Mailbox s_mail[STAGES];
+  __shared__ Mailbox s_mail[QS];
   __shared__ int s_split[STAGES][NSPLIT];
   __shared__ int s_wcnt[2][NWARPS];
   __shared__ volatile unsigned int s_n_iter;            // tiles this CTA ended up processing (set when the END marker arrives)
@@ -185,10 +193,13 @@ setop2_stream_kernel (const TileArgs args)
     for (int s = 0; s < STAGES; s++) {
       mbar_init (&bar_full[s], 1);
       mbar_init (&bar_split[s], 1);
+      mbar_init (&bar_empty[s], COUNT_ONLY ? NWARPS : STORE_WARPS);
+    }
+#pragma unroll
+    for (int s = 0; s < QS; s++) {
       mbar_init (&bar_comp[s], NWARPS);
       mbar_init (&bar_agg[s], 1);
       mbar_init (&bar_base[s], 1);
-      mbar_init (&bar_empty[s], COUNT_ONLY ? NWARPS : STORE_WARPS);
       mbar_init (&bar_done[s], STORE_WARPS);
     }
     s_n_iter = 0xffffffffu;
@@ -286,7 +297,7 @@ setop2_stream_kernel (const TileArgs args)
         // out of work: send an END marker through EVERY stage, in order and under the normal stage protocol
         // (each look-back warp owns one stage and must see its own marker; a barrier may never be advanced
         // twice before its waiter has looked)
-        for (int q = 0; q < (COUNT_ONLY ? 1 : STAGES); q++) {
+        for (int q = 0; q < (ONE_END ? 1 : STAGES); q++) {
           if (q > 0) helper_wait (&bar_empty[s], ph ^ 1u);
           s_meta[s].tile = TILE_END;
           mbar_arrive (&bar_full[s]);
@@ -411,7 +422,7 @@ setop2_stream_kernel (const TileArgs args)
       __syncwarp ();
       if (lane == 0) mbar_arrive (&bar_split[s]);
       if (sprof) { t_sfull += s1 - s0; t_ssearch += clock64 () - s1; }
-      if (m.tile == TILE_END && ++n_end == (COUNT_ONLY ? 1 : STAGES)) break;
+      if (m.tile == TILE_END && ++n_end == (ONE_END ? 1 : STAGES)) break;
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     if (sprof && lane == 0) {        // experiments: how long the splitter waits for the TMA, how long its searches take
@@ -429,7 +440,7 @@ setop2_stream_kernel (const TileArgs args)
     const int s = warp - LOOKBACK_WARP0;
     uint32_t ph = 0;
     LookbackStats stats = {0, 0, 0, 0};
-    for (uint32_t it = (uint32_t) s;; it += STAGES, ph ^= 1u) {
+    for (uint32_t it = (uint32_t) s;; it += QS, ph ^= 1u) {
       helper_wait (&bar_agg[s], ph);
       if (it >= s_n_iter) break;                  // the END marker, not a tile
       const uint64_t tile = s_mail[s].tile;
@@ -465,8 +476,9 @@ setop2_stream_kernel (const TileArgs args)
       const uint64_t base = s_mail[s].base;
       const int cnt = s_mail[s].cnt;
       const bool from_side = SIDE && s_mail[s].side != 0;
-      const uint64_t *sk = from_side ? side_keys (s) : stage_keys (s);
-      const uint32_t *sc = from_side ? side_cnts (s) : stage_cnts (s);
+      const int stage = s_mail[s].stage;
+      const uint64_t *sk = from_side ? side_keys (s) : stage_keys (stage);
+      const uint32_t *sc = from_side ? side_cnts (s) : stage_cnts (stage);
       if (args.debug & 8) {
         // experiment: no stores
       } else if (base + (uint64_t) cnt > args.out_capacity[stream]) {
@@ -498,10 +510,10 @@ setop2_stream_kernel (const TileArgs args)
 #endif
       __syncwarp ();
       if (lane == 0) {
-        if (!from_side) mbar_arrive (&bar_empty[s]);       // (a tile in a side buffer gave its stage back long ago)
+        if (!from_side) mbar_arrive (&bar_empty[stage]);   // (a tile in a side buffer gave its stage back long ago)
         if (SIDE) mbar_arrive (&bar_done[s]);
       }
-      if (++s == STAGES) { s = 0; ph ^= 1u; }
+      if (++s == QS) { s = 0; ph ^= 1u; }
     }
     return;
   }
@@ -511,6 +523,8 @@ setop2_stream_kernel (const TileArgs args)
   unsigned long long acc_n = 0, acc_sum = 0;   // this thread's share of the header totals
   int s = 0, n_end = 0;
   uint32_t ph = 0;
+  int q = 0;                  // the tile's output slot and its phase (the same as s / ph unless there are more slots than stages)
+  uint32_t qph = 0;
   const bool prof = (args.debug & 32) != 0;
   long long t_wait = 0, t_search = 0, t_merge = 0, t_scan = 0, t_scatter = 0, n_tiles_done = 0;
   for (uint32_t it = 0;; it++) {
@@ -522,15 +536,20 @@ setop2_stream_kernel (const TileArgs args)
       if (COUNT_ONLY) break;
       // END markers arrive on S consecutive stages; pass each one on to that stage's look-back warp
       // (and the first one to the store warps)
-      if (SIDE) mbar_wait (&bar_done[s], ph ^ 1u);        // the store warps may still be reading the slot's previous mailbox
-      if (tid == 0) {
-        if (it < s_n_iter) s_n_iter = it;
-        s_mail[s].tile = TILE_END;
-        mbar_arrive (&bar_agg[s]);
+      // every output slot passes an END marker on (each look-back warp owns a slot, the store warps take the first): one
+      // per END marker when slots and stages coincide, all at once when the producer sends a single marker
+      for (int e = 0; e < (QS != S ? QS : 1); e++) {
+        if (SIDE) mbar_wait (&bar_done[q], qph ^ 1u);        // the store warps may still be reading the slot's previous mailbox
+        if (tid == 0) {
+          if (it < s_n_iter) s_n_iter = it;
+          s_mail[q].tile = TILE_END;
+          mbar_arrive (&bar_agg[q]);
+        }
+        __syncwarp ();
+        if (lane == 0) mbar_arrive (&bar_comp[q]);
+        if (++q == QS) { q = 0; qph ^= 1u; }
       }
-      __syncwarp ();
-      if (lane == 0) mbar_arrive (&bar_comp[s]);
-      if (++n_end == STAGES) break;
+      if (QS != S || ++n_end == STAGES) break;
       if (++s == STAGES) { s = 0; ph ^= 1u; }
       continue;
     }
@@ -604,12 +623,13 @@ setop2_stream_kernel (const TileArgs args)
     const int warp_prefix = __shfl_sync (0xffffffffu, wincl - wv, warp);
 #endif
     const bool to_side = SIDE && tile_cnt <= Cfg::SIDE_CAP;
-    if (SIDE) mbar_wait (&bar_done[s], ph ^ 1u);      // the slot's previous tile has been stored: its mailbox and side buffer are free
+    if (SIDE) mbar_wait (&bar_done[q], qph ^ 1u);     // the slot's previous tile has been stored: its mailbox and side buffer are free
     if (tid == 0) {
-      s_mail[s].tile = m.tile;
-      s_mail[s].cnt = tile_cnt;
-      s_mail[s].side = to_side ? 1 : 0;
-      mbar_arrive (&bar_agg[s]);    // the look-back warp takes it from here
+      s_mail[q].tile = m.tile;
+      s_mail[q].cnt = tile_cnt;
+      s_mail[q].side = to_side ? 1 : 0;
+      s_mail[q].stage = s;
+      mbar_arrive (&bar_agg[q]);    // the look-back warp takes it from here
     }
     uint64_t *dk = sk;
     uint32_t *dc = sc;
@@ -617,8 +637,8 @@ setop2_stream_kernel (const TileArgs args)
       // few survivors: they go to the stage's side buffer and the stage itself returns to the producer NOW (every consumer
       // read its inputs before the named barrier above), one look-back + store earlier than otherwise
       if (tid == 0) mbar_arrive_n (&bar_empty[s], STORE_WARPS);      // standing in for the store warps, which never touch this stage
-      dk = side_keys (s);
-      dc = side_cnts (s);
+      dk = side_keys (q);
+      dc = side_cnts (q);
     }
 
     // compact this tile's survivors (to the front of its own stage buffer unless to_side), then hand them to the store warps
@@ -632,10 +652,11 @@ setop2_stream_kernel (const TileArgs args)
       }
     }
     __syncwarp ();
-    if (lane == 0) mbar_arrive (&bar_comp[s]);
+    if (lane == 0) mbar_arrive (&bar_comp[q]);
 
     if (prof) { const long long c5 = clock64 (); t_scan += c4 - c3; t_scatter += c5 - c4; }
     if (++s == STAGES) { s = 0; ph ^= 1u; }
+    if (++q == QS) { q = 0; qph ^= 1u; }
   }
   if (prof && lane == 0) {       // experiments: per-phase cycles of the consumer warps
     atomicAdd (&args.hdr->dbg[0], (unsigned long long) t_wait); atomicAdd (&args.hdr->dbg[1], (unsigned long long) t_search);
@@ -665,7 +686,7 @@ setop2_stream_kernel (const TileArgs args)
 }
 
 // ---- launch ------------------------------------------------------------------------------------
-template <int NC, int VT, int S, int FAST, bool CO, bool SIDE = false>
+template <int NC, int VT, int S, int FAST, bool CO, int SIDE = 0>
 cudaError_t launch_stream_one (const TileArgs &args, int sm_count, cudaStream_t st)
 {
   using Cfg = StreamCfg<NC, VT, S, SIDE>;
@@ -729,14 +750,26 @@ cudaError_t launch_setop2_stream (const TileArgs &args, int consumers, int items
   if (args.n_tiles == 0) return cudaSuccess;
   const int fast = select_fast_path (args.p, args.stream0);
   // outputs that are sparse as a rule (intersections, differences) at the default tile: the side-buffer variant, 3 stages
-  if (!count_only && consumers == 512 && items == 9 && (g_stream_side == 2 || (g_stream_side == 1 && args.side_hint))) {
-    if (g_stream_side == 2 && fast == FAST_U_ADD) return launch_stream_one<512, 9, 3, FAST_U_ADD, false, true> (args, sm_count, st);      // (measurements)
-    switch (fast) {
-    case FAST_I_MIN:  return launch_stream_one<512, 9, 3, FAST_I_MIN, false, true> (args, sm_count, st);
-    case FAST_D_SUB:  return launch_stream_one<512, 9, 3, FAST_D_SUB, false, true> (args, sm_count, st);
-    case FAST_D2_SUB: return launch_stream_one<512, 9, 3, FAST_D2_SUB, false, true> (args, sm_count, st);
-    case FAST_NI_MIN: return launch_stream_one<512, 9, 3, FAST_NI_MIN, false, true> (args, sm_count, st);
-    default: break;
+  if (!count_only && consumers == 512 && items == 9 && (g_stream_side >= 2 || (g_stream_side == 1 && args.side_hint))) {
+    if (g_stream_side == 2 && fast == FAST_U_ADD) return launch_stream_one<512, 9, 3, FAST_U_ADD, false, 1> (args, sm_count, st);      // (measurements)
+    // side_hint 1: sparse output, three stages + side buffers of a third of a tile; 2: medium density, two stages + three
+    // side buffers of 61 % of a tile (option "stream_side" 2 / 3 force the one / the other)
+    if ((g_stream_side == 1 && args.side_hint == 2) || g_stream_side == 3) {
+      switch (fast) {
+      case FAST_I_MIN:  return launch_stream_one<512, 9, 2, FAST_I_MIN, false, 2> (args, sm_count, st);
+      case FAST_D_SUB:  return launch_stream_one<512, 9, 2, FAST_D_SUB, false, 2> (args, sm_count, st);
+      case FAST_D2_SUB: return launch_stream_one<512, 9, 2, FAST_D2_SUB, false, 2> (args, sm_count, st);
+      case FAST_NI_MIN: return launch_stream_one<512, 9, 2, FAST_NI_MIN, false, 2> (args, sm_count, st);
+      default: break;
+      }
+    } else {
+      switch (fast) {
+      case FAST_I_MIN:  return launch_stream_one<512, 9, 3, FAST_I_MIN, false, 1> (args, sm_count, st);
+      case FAST_D_SUB:  return launch_stream_one<512, 9, 3, FAST_D_SUB, false, 1> (args, sm_count, st);
+      case FAST_D2_SUB: return launch_stream_one<512, 9, 3, FAST_D2_SUB, false, 1> (args, sm_count, st);
+      case FAST_NI_MIN: return launch_stream_one<512, 9, 3, FAST_NI_MIN, false, 1> (args, sm_count, st);
+      default: break;
+      }
     }
   }
 #define X(NC, VT, S)                                                                                        \

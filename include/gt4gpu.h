@@ -121,7 +121,8 @@ int gt4gpu_set_tile (int threads, int items_per_thread);
  * "use_fused" (0: several outputs take one pass of the single-output kernel each instead of the one-read kernel),
  * "use_kway" (0: N-list calls run as a tree / chain of two-list merges, 1: unions take the single-pass kernel,
  * 2: intersections too) and "stream_side" (0: sparse outputs never take the side-buffer variant of the single-output
- * kernel, 1: when a density sample of the call says so, 2: always where the variant exists).  None of them changes a result. */
+ * kernel, 1: when a density sample of the call says so, 2 / 3: always the three-stage / the two-stage variant where it
+ * exists).  None of them changes a result. */
 int gt4gpu_set_option (const char *name, int value);
 /* Device time of the most recent merge call on this thread, from CUDA events on the launch stream:
  * partition kernel, tile kernel, and the launch count (each may be NULL). */

@@ -6,7 +6,7 @@ name=$1; shift
 root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/genometester4_b200/csrc
 out=$root/build/variants; mkdir -p $out/$name
-flags="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --extended-lambda -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -diag-suppress 177 $*"
+flags="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --extended-lambda -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -diag-suppress 177,128 $*"
 for f in gt4gpu_kernels gt4gpu_stream_kernel gt4gpu_kway_kernel gt4gpu_fused_kernel gt4gpu_sort_kernel gt4gpu_fasta_kernel gt4gpu_api; do
   nvcc $flags -c -o $out/$name/$f.o $src/$f.cu &
 done

@@ -147,13 +147,15 @@ def test_stream_kernel_every_shape_rule_and_semantics(g, oracle, shape):
         g.set_option("stream_shape", 51209)
 
 
-def test_stream_kernel_side_buffer_variant_forced(g, oracle):
-    """The side-buffer variant of the stream kernel (3 stages + a side buffer per stage; sparse tiles give their stage back
-    right after the merge, fuller tiles keep it) is chosen from a density sample on big calls only; here it is forced
-    (stream_side = 2) on inputs of hundreds of tiles whose outputs are sparse, mixed and dense (identical lists: every
-    tile overflows its side buffer), for the four outputs, cut-offs, and the N-list intersection chain."""
+@pytest.mark.parametrize("variant", [2, 3])
+def test_stream_kernel_side_buffer_variant_forced(g, oracle, variant):
+    """The side-buffer variants of the stream kernel (2: three stages + a side buffer of a third of a tile per stage; 3: two
+    stages + three output slots with side buffers of 61 % of a tile; sparse tiles give their stage back right after the
+    merge, fuller tiles keep it) are chosen from a density sample on big calls only; here they are forced (stream_side = 2 / 3)
+    on inputs of hundreds of tiles whose outputs are sparse, mixed and dense (identical lists: every tile overflows its side
+    buffer), for the four outputs, cut-offs, and the N-list intersection chain."""
     g.set_option("stream_shape", 51209)
-    g.set_option("stream_side", 2)
+    g.set_option("stream_side", variant)
     try:
         for seed, (na, nb, both), kind in ((21, (300_001, 250_003, 120_000), "tail"), (22, (400_000, 400_000, 400_000), "small"),
                                            (23, (500_000, 480_000, 20_000), "tail"), (24, (3, 200_001, 2), "tail"), (25, (150_000, 7, 0), "huge"),
