@@ -27,6 +27,13 @@
 // ticket, so a tile's predecessors are always owned by CTAs that are already running and the
 // look-back cannot deadlock whatever the residency of the grid.
 //
+// Side-buffer variants (template parameter SIDE, chosen per call from a density sample, gt4gpu_api.cu): an intersection or
+// difference keeps few of a tile's slots, so its survivors are compacted into a small side buffer of the tile's output
+// slot and the stage returns to the producer right after the merge instead of waiting for the look-back and the store.
+// SIDE == 1: three stages, a side buffer of a third of a tile per stage; SIDE == 2: two stages and three output slots
+// (mailbox, barriers, look-back warp, side buffer of 61 % of a tile) that are not tied to a stage.  A tile that keeps
+// more than its side buffer holds compacts in place and keeps its stage, exactly as in the plain kernel.
+//
 // HBM-bound integer work: no tensor cores.  Algorithmic traffic 12 B per input record + 12 B per
 // output record.
 #include <cuda_runtime.h>
